@@ -1,0 +1,196 @@
+/*
+ * pemspgemm.h — C ABI of the B200-native SpGEMM engine (libpemspgemm.so).
+ *
+ * The reference (stckvrflw/pem-spgemm, /root/reference) has no library, plugin or FFI
+ * layer: conversion, the three SpGEMM steps, timing and the result dump are inline in
+ * `main` (spgemm.cu:720-1568).  This header cuts that function at its stage boundaries so
+ * that a host program (the `pemspgemm` CLI in this repo, the reference's own `main`, a
+ * ctypes/cgo/JNI binding) can call the hot path as a drop-in.  Each entry point names the
+ * region of the reference it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns PEM_OK (0) or a
+ * negative pem_status and never calls exit(); `pem_last_error` gives the message.  A
+ * context owns one CUDA stream and one stream-ordered memory pool (cudaMemPool_t) on one
+ * device; it is not thread-safe; use one context per GPU.  Opaque handles own device
+ * memory from the context's pool and must be freed through this ABI before the context.
+ * There is no CPU fallback: without a CUDA device pem_ctx_create fails.
+ */
+#ifndef PEMSPGEMM_H
+#define PEMSPGEMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEM_TILE 16 /* tile edge, spgemm.cu:727 */
+
+typedef enum pem_status {
+    PEM_OK = 0,
+    PEM_ERR_CUDA = -1,       /* a CUDA runtime call failed (message has the call site)      */
+    PEM_ERR_ARG = -2,        /* bad argument (null handle, negative size, shape mismatch)   */
+    PEM_ERR_RANGE = -3,      /* a COO coordinate is outside rows x cols                     */
+    PEM_ERR_DUPLICATE = -4,  /* the COO input holds the same (i,j) twice (reference: UB)    */
+    PEM_ERR_LIMIT = -5,      /* a size exceeds what the engine supports (see message)       */
+    PEM_ERR_NO_DEVICE = -6,  /* no usable CUDA device                                       */
+    PEM_ERR_IO = -7          /* file could not be read / parsed / written                   */
+} pem_status;
+
+typedef struct pem_ctx pem_ctx;       /* stream + memory pool + scratch, one per GPU */
+typedef struct pem_tiled pem_tiled;   /* a matrix in 16x16 tiled-CSR form */
+typedef struct pem_result pem_result; /* C (or a tile-row panel of C) in tiled form */
+
+/* Engine options (pem_ctx_set_option). */
+typedef enum pem_option {
+    /* 0 (default): step 1 drops (A tile, B tile) pairs whose 16x16 boolean product is empty, so
+     *    C' holds exactly the non-empty tiles of C.
+     * 1: reference-faithful C': every structurally reachable tile and pair is kept, including
+     *    empty ones (spgemm.cu:271-384 works on the tile structure only; "C tiles" in the
+     *    reference's report counts them, spgemm.cu:1420).  C itself is identical either way. */
+    PEM_OPT_KEEP_EMPTY_TILES = 1,
+    /* step-1 accumulator choice per tile row: 0 = automatic (default), 1 = force the bitmap
+     * (SPA) path, 2 = force the hash path.  Replaces the reference's global switch
+     * `B_tileCols > 512*32` (spgemm.cu:1142). */
+    PEM_OPT_STEP1_PATH = 2
+} pem_option;
+
+/* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are
+ * host clocks around the call with the stream drained on both sides (the reference's
+ * pem_spgemm_time, spgemm.cu:1136,1340). */
+typedef struct pem_times {
+    double convert_kernel_ms; /* tile build kernel only  == A/B_conversion_kernel_time (spgemm.cu:938-978) */
+    double convert_total_ms;  /* whole COO->tiled conversion incl. H2D copies (wall)                       */
+    double step1_ms;          /* tile-level symbolic  == step1_time (spgemm.cu:1141-1218)                  */
+    double step2_ms;          /* mask symbolic        == step2_time (spgemm.cu:1344-1350)                  */
+    double step3_ms;          /* numeric              == step3_time (spgemm.cu:1348)                       */
+    double kernel_ms;         /* step1+step2+step3    == pem_spgemm_kernel_time (spgemm.cu:1353)           */
+    double total_ms;          /* wall for the call    == pem_spgemm_time (spgemm.cu:1352)                  */
+    double malloc_ms;         /* total - kernel       == pem_spgemm_malloc_time (spgemm.cu:1354)           */
+} pem_times;
+
+typedef struct pem_tiled_info {
+    int32_t rows, cols;           /* after the optional transpose */
+    int64_t nnz;
+    int32_t tile_rows, tile_cols; /* ceil(rows/16), ceil(cols/16), spgemm.cu:840-843 */
+    int32_t tiles;                /* non-empty tiles (cntA / cntB, spgemm.cu:871,885) */
+} pem_tiled_info;
+
+typedef struct pem_result_info {
+    int32_t tile_row_begin, tile_row_end; /* the panel of A' tile rows this result covers */
+    int32_t rows, cols;                   /* shape of the full C */
+    int64_t tiles;                        /* C' tiles        ("C tiles",  spgemm.cu:1420) */
+    int64_t pairs;                        /* (A tile,B tile) pairs (d_pairs_count, spgemm.cu:1246) */
+    int64_t nnz;                          /* nnz of C         ("C nnz",   spgemm.cu:1421) */
+    int64_t tile_products;                /* tile-level intermediate products examined by step 1 */
+} pem_result_info;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Replaces the stream / RMM pool setup at spgemm.cu:757-758,808-817. */
+int pem_ctx_create(pem_ctx** out, int device);
+void pem_ctx_destroy(pem_ctx* ctx);
+const char* pem_last_error(const pem_ctx* ctx); /* valid until the next call on ctx */
+int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value);
+void* pem_ctx_stream(pem_ctx* ctx);             /* the cudaStream_t all work is enqueued on */
+int pem_ctx_sync(pem_ctx* ctx);
+/* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
+int64_t pem_ctx_launch_count(const pem_ctx* ctx);
+/* Bytes currently reserved by the context's pool (diagnostic). */
+int64_t pem_ctx_pool_bytes(const pem_ctx* ctx);
+
+/* ---- conversion: COO -> tiled CSR ----------------------------------------------------- */
+/* Replaces spgemm.cu:821-1066 (decide_which_tile, the thrust sort/unique/reduce pipeline,
+ * generate_tiles_csr, __transpose_B_mask, tile-level CSR build).  I/J/V may be host or device
+ * pointers (0-based, any order, no duplicates).  transpose != 0 converts the transposed matrix
+ * (the CLI's B = A^T mode, spgemm.cu:788-792).  times may be NULL. */
+int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
+                    const int32_t* I, const int32_t* J, const double* V, int transpose,
+                    pem_tiled** out, pem_times* times);
+int pem_tiled_info_get(const pem_tiled* t, pem_tiled_info* info);
+void pem_tiled_free(pem_ctx* ctx, pem_tiled* t);
+
+/* Arrays of a tiled matrix, copied to host for tests / interop. */
+typedef enum pem_tiled_array {
+    PEM_T_VALS = 0,         /* double  [nnz]      *tiles_vals      */
+    PEM_T_TILE_NNZ_PTR = 1, /* uint32  [tiles+1]  *_perTileNnz     */
+    PEM_T_MASKS = 2,        /* uint16  [tiles*16] *tiles_masks     */
+    PEM_T_ROW_PTR = 3,      /* uint8   [tiles*16] *tiles_rowPtr    */
+    PEM_T_MASKS_T = 4,      /* uint16  [tiles*16] Btiles_transposed_mask */
+    PEM_T_TILE_ROW_PTR = 5, /* int32   [tile_rows+1] _X_tileRowPtr */
+    PEM_T_TILE_COL_IDX = 6, /* int32   [tiles]    _X_tileColIdx    */
+    PEM_T_TILE_ROW_IDX = 7, /* int32   [tiles]    tile row of each tile */
+    PEM_T_COL_OCC = 8,      /* uint16  [tiles]    OR of the tile's row masks    */
+    PEM_T_ROW_OCC = 9       /* uint16  [tiles]    OR of the tile's column masks */
+} pem_tiled_array;
+int pem_tiled_get(pem_ctx* ctx, const pem_tiled* t, int which, void* host_dst, size_t bytes);
+/* Device pointer of the same arrays (no copy; owned by the handle). */
+const void* pem_tiled_device_ptr(const pem_tiled* t, int which);
+
+/* ---- flop count and panel partition ---------------------------------------------------- */
+/* flop = sum over a_ik of nnz(B row k); replaces the host thread at spgemm.cu:1068-1079. */
+int pem_count_flop(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, uint64_t* flop);
+/* Split A's tile rows into nparts contiguous panels with balanced flop: bounds[0]=0,
+ * bounds[nparts]=tile_rows (north_star: row-block tile-row panels by per-row flop count). */
+int pem_partition_panels(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, int nparts,
+                         int32_t* bounds /* nparts+1 */);
+
+/* ---- SpGEMM --------------------------------------------------------------------------- */
+/* C = A*B: steps 1-3 with allocation, i.e. one iteration of the loop at spgemm.cu:1133-1357. */
+int pem_spgemm(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result** C, pem_times* times);
+/* Same for the panel of A' tile rows [tile_row_begin, tile_row_end) (multi-GPU shards). */
+int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
+                     int32_t tile_row_begin, int32_t tile_row_end, pem_result** C, pem_times* times);
+/* Stage-level entry points (tests, ncu).  step1 creates the result handle; each later stage
+ * requires the previous one.
+ *   step1 : C' structure + ordered (A tile,B tile) pair lists
+ *           (spgemm.cu:271-384 / NSPARSE hash path + pem_spgemm_step2_search_pairs, :387-497)
+ *   step2 : C tile masks, per-tile nnz, scan, rowColIdx
+ *           (pem_spgemm_step2_compute_CMasksAndOffsets :499-550, ..._CrowColIdx :552-591)
+ *   step3 : values (pem_spgemm_step3_accumulate :593-661)                                  */
+int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
+                       int32_t tile_row_begin, int32_t tile_row_end, pem_result** C);
+int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C);
+int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C);
+
+int pem_result_info_get(const pem_result* C, pem_result_info* info);
+void pem_result_free(pem_ctx* ctx, pem_result* C);
+
+typedef enum pem_result_array {
+    PEM_R_ROW_PTR = 0,      /* int64  [panel tile rows+1]  _C_rowPtr            */
+    PEM_R_TILE_ROW = 1,     /* int32  [tiles]              _C_tileRowIdx        */
+    PEM_R_TILE_COL = 2,     /* int32  [tiles]              _C_tileColIdx        */
+    PEM_R_PAIR_PTR = 3,     /* int64  [tiles+1]            pairs_insertion_offset */
+    PEM_R_PAIRS_A = 4,      /* int32  [pairs]              d_pairs_a            */
+    PEM_R_PAIRS_B = 5,      /* int32  [pairs]              d_pairs_b            */
+    PEM_R_MASKS = 6,        /* uint16 [tiles*16]           Ctiles_mask (row r at index t*16+r) */
+    PEM_R_TILE_NNZ_PTR = 7, /* int64  [tiles+1]            _C_perTileNnz        */
+    PEM_R_ROW_COL_IDX = 8,  /* uint8  [nnz]                Ctiles_rowColIdx     */
+    PEM_R_VALS = 9          /* double [nnz]                Ctiles_vals          */
+} pem_result_array;
+int pem_result_get(pem_ctx* ctx, const pem_result* C, int which, void* host_dst, size_t bytes);
+const void* pem_result_device_ptr(const pem_result* C, int which);
+
+/* Tiled C -> COO sorted by (row, col): sanitize_C + stable_sort + D2H (spgemm.cu:1493-1543).
+ * rows/cols/vals are HOST buffers of pem_result_info.nnz entries (any may be NULL to skip). */
+int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, double* vals);
+/* Same, but into DEVICE buffers, plus CSR row pointer (int64[rows_in_panel*16+1], may be NULL). */
+int pem_result_to_coo_device(pem_ctx* ctx, const pem_result* C, int32_t* d_rows, int32_t* d_cols,
+                             double* d_vals, int64_t* d_row_ptr);
+/* Sum and sum of absolute values of C's values, reduced on the device (cheap result read-back
+ * for end-to-end timing and smoke tests). */
+int pem_result_checksum(pem_ctx* ctx, const pem_result* C, double* sum, double* abs_sum);
+
+/* ---- Matrix Market I/O (host side; replaces fast_matrix_market use at spgemm.cu:43-110) ---- */
+/* Reads coordinate real/integer/pattern/complex(real part) general/symmetric files into
+ * malloc'ed arrays (free with pem_free_host).  Symmetric files are expanded. */
+int pem_mtx_read(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz,
+                 int32_t** I, int32_t** J, double** V, int* is_symmetric, char* err, size_t err_len);
+int pem_mtx_write(const char* path, int32_t rows, int32_t cols, int64_t nnz,
+                  const int32_t* I, const int32_t* J, const double* V);
+void pem_free_host(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEMSPGEMM_H */

@@ -1,0 +1,390 @@
+// COO -> 16x16 tiled CSR on the GPU, plus flop counting and the flop-balanced panel split.
+//
+// Replaces /root/reference/spgemm.cu:821-1066: decide_which_tile (:112-135), the thrust
+// sort / unique_count / reduce_by_key / scan / unique census (:866-892), the tuple merge sort
+// to CSR (:894-928), generate_tiles_csr with its 256 binary searches per tile (:137-226),
+// __transpose_B_mask (:228-258) and the tile-level CSR build (:985-1031).
+//
+// B200 design: ONE radix sort.  Every nonzero gets a 64-bit key
+//     (tileRow, tileCol, r, c)  packed as  tileRow << (cb+8) | tileCol << 8 | r << 4 | c
+// and is sorted together with its value over exactly the bits in use (8 + cb + rb, 5-6 radix
+// passes).  The sorted value array IS the tiled value array (tile-major, row-major inside a
+// tile); tile boundaries are the positions where key>>8 changes; one thread per tile then folds
+// its keys' low bytes into the row masks, column masks, row pointers and occupancy words with
+// 64-bit register bit-sets (no binary search, no shared memory, no CSR intermediate).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include <chrono>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace {
+
+__device__ __forceinline__ int bits_for(int n)
+{  // bits needed to hold values 0..n-1 (at least 1)
+    return n <= 1 ? 1 : 32 - __clz(n - 1);
+}
+inline int h_bits_for(int64_t n)
+{
+    int b = 1;
+    while ((int64_t(1) << b) < n) ++b;
+    return b;
+}
+
+// One thread per nonzero: range check, optional transpose, key packing.
+__global__ void __launch_bounds__(256)
+k_make_keys(const int32_t* __restrict__ I, const int32_t* __restrict__ J, int64_t nnz,
+            int rows, int cols, int transpose, int cb, uint64_t* __restrict__ keys,
+            int64_t* __restrict__ scalars)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; e < nnz; e += stride) {
+        int i = I[e], j = J[e];
+        if (transpose) { int t = i; i = j; j = t; }
+        uint64_t key;
+        if ((unsigned)i >= (unsigned)rows || (unsigned)j >= (unsigned)cols) {
+            atomicOr((unsigned long long*)&scalars[SC_ERR], 1ull);
+            key = 0;
+        } else {
+            key = ((uint64_t)(i >> 4) << (cb + 8)) | ((uint64_t)(j >> 4) << 8) | (uint64_t)(((i & 15) << 4) | (j & 15));
+        }
+        keys[e] = key;
+    }
+}
+
+// predicate for the tile census: position e starts a new tile
+struct HeadPred {
+    const uint64_t* keys;
+    __device__ __forceinline__ bool operator()(uint32_t e) const
+    {
+        return e == 0 || (keys[e] >> 8) != (keys[e - 1] >> 8);
+    }
+};
+
+__device__ __forceinline__ void set_bit256(uint64_t (&w)[4], unsigned b)
+{
+    uint64_t bit = 1ull << (b & 63);
+    unsigned wi = b >> 6;
+    w[0] |= wi == 0 ? bit : 0ull;
+    w[1] |= wi == 1 ? bit : 0ull;
+    w[2] |= wi == 2 ? bit : 0ull;
+    w[3] |= wi == 3 ? bit : 0ull;
+}
+
+__device__ __forceinline__ unsigned fold16(const uint64_t (&w)[4])
+{
+    uint64_t x = w[0] | w[1] | w[2] | w[3];
+    x |= x >> 32;
+    x |= x >> 16;
+    return (unsigned)(x & 0xFFFFu);
+}
+
+// One thread per tile.  keys are sorted; start[t] is the first nonzero of tile t.
+__global__ void __launch_bounds__(128)
+k_build_tiles(const uint64_t* __restrict__ keys, uint32_t* __restrict__ start, int cnt, uint32_t nnz,
+              int cb, int tile_rows,
+              uint16_t* __restrict__ masks, uint16_t* __restrict__ masks_t, uint8_t* __restrict__ row_ptr,
+              int32_t* __restrict__ tile_col, int32_t* __restrict__ tile_row, int32_t* __restrict__ tile_row_ptr,
+              uint16_t* __restrict__ col_occ, uint16_t* __restrict__ row_occ, int64_t* __restrict__ scalars)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    uint32_t s = start[t];
+    uint32_t e = (t + 1 < cnt) ? start[t + 1] : nnz;
+    uint64_t w[4] = {0, 0, 0, 0}, wt[4] = {0, 0, 0, 0};
+    uint64_t k0 = keys[s], prev = ~0ull;
+    bool dup = false;
+    for (uint32_t x = s; x < e; ++x) {
+        uint64_t k = keys[x];
+        dup |= (k == prev);
+        prev = k;
+        unsigned rc = (unsigned)(k & 255u);
+        set_bit256(w, rc);                                  // bit r*16+c : row masks
+        set_bit256(wt, ((rc & 15u) << 4) | (rc >> 4));      // bit c*16+r : column masks
+    }
+    if (dup) atomicOr((unsigned long long*)&scalars[SC_ERR], 2ull);
+
+    // uint16 mask[16] in memory == four little-endian 64-bit words
+    uint4* m4 = reinterpret_cast<uint4*>(masks + (size_t)t * 16);
+    m4[0] = make_uint4((unsigned)w[0], (unsigned)(w[0] >> 32), (unsigned)w[1], (unsigned)(w[1] >> 32));
+    m4[1] = make_uint4((unsigned)w[2], (unsigned)(w[2] >> 32), (unsigned)w[3], (unsigned)(w[3] >> 32));
+    uint4* t4 = reinterpret_cast<uint4*>(masks_t + (size_t)t * 16);
+    t4[0] = make_uint4((unsigned)wt[0], (unsigned)(wt[0] >> 32), (unsigned)wt[1], (unsigned)(wt[1] >> 32));
+    t4[1] = make_uint4((unsigned)wt[2], (unsigned)(wt[2] >> 32), (unsigned)wt[3], (unsigned)(wt[3] >> 32));
+
+    // row pointers: exclusive scan of the 16 row popcounts, one byte each (max 240)
+    unsigned rp[4];
+    unsigned run = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int r = q * 4 + b;
+            word |= run << (8 * b);
+            run += __popcll(w[r >> 2] & (0xFFFFull << ((r & 3) * 16)));
+        }
+        rp[q] = word;
+    }
+    *reinterpret_cast<uint4*>(row_ptr + (size_t)t * 16) = make_uint4(rp[0], rp[1], rp[2], rp[3]);
+
+    col_occ[t] = (uint16_t)fold16(w);
+    row_occ[t] = (uint16_t)fold16(wt);
+
+    int tr = (int)(k0 >> (cb + 8));
+    int tc = (int)((k0 >> 8) & ((1ull << cb) - 1));
+    tile_col[t] = tc;
+    tile_row[t] = tr;
+    // tile-level CSR row pointer: this tile opens every tile row after the previous tile's
+    int prev_tr = (t == 0) ? -1 : (int)(keys[start[t - 1]] >> (cb + 8));
+    for (int r = prev_tr + 1; r <= tr; ++r) tile_row_ptr[r] = t;
+    if (t == cnt - 1) {
+        for (int r = tr + 1; r <= tile_rows; ++r) tile_row_ptr[r] = cnt;
+        start[cnt] = nnz;
+    }
+}
+
+// per-row nonzero counts of a tiled matrix (thread per tile, 16 atomics at most)
+__global__ void __launch_bounds__(256)
+k_row_nnz(const uint16_t* __restrict__ masks, const int32_t* __restrict__ tile_row, int cnt,
+          uint32_t* __restrict__ row_nnz)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const uint4* m4 = reinterpret_cast<const uint4*>(masks + (size_t)t * 16);
+    uint4 a = m4[0], b = m4[1];
+    unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    int base = tile_row[t] * 16;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        unsigned m = (w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
+        if (m) atomicAdd(&row_nnz[base + r], (unsigned)__popc(m));
+    }
+}
+
+// flop of one A tile = sum_k (nnz of A column k in the tile) * nnz(B row 16*tc + k); summed per tile row
+__global__ void __launch_bounds__(256)
+k_tile_flop(const uint16_t* __restrict__ masks_t, const int32_t* __restrict__ tile_row,
+            const int32_t* __restrict__ tile_col, int cnt, const uint32_t* __restrict__ b_row_nnz, int b_rows,
+            unsigned long long* __restrict__ tile_row_flop)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const uint4* m4 = reinterpret_cast<const uint4*>(masks_t + (size_t)t * 16);
+    uint4 a = m4[0], b = m4[1];
+    unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    int base = tile_col[t] * 16;
+    unsigned long long f = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        unsigned m = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+        if (m && base + k < b_rows) f += (unsigned long long)__popc(m) * b_row_nnz[base + k];
+    }
+    if (f) atomicAdd(&tile_row_flop[tile_row[t]], f);
+}
+
+bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int tile_row_flops(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, unsigned long long** d_out)
+{
+    uint32_t* b_row_nnz = nullptr;
+    unsigned long long* trf = nullptr;
+    PEM_TRY(pem_alloc(ctx, &b_row_nnz, (size_t)B->tile_rows * 16));
+    PEM_TRY(pem_alloc(ctx, &trf, (size_t)A->tile_rows));
+    PEM_CK(cudaMemsetAsync(b_row_nnz, 0, (size_t)(B->tile_rows ? B->tile_rows : 1) * 16 * 4, ctx->stream));
+    PEM_CK(cudaMemsetAsync(trf, 0, (size_t)(A->tile_rows ? A->tile_rows : 1) * 8, ctx->stream));
+    if (B->tiles) {
+        k_row_nnz<<<pem_div_up(B->tiles, 256), 256, 0, ctx->stream>>>(B->masks, B->tile_row_idx, B->tiles, b_row_nnz);
+        PEM_LAUNCHED();
+    }
+    if (A->tiles) {
+        k_tile_flop<<<pem_div_up(A->tiles, 256), 256, 0, ctx->stream>>>(A->masks_t, A->tile_row_idx, A->tile_col_idx,
+                                                                        A->tiles, b_row_nnz, B->rows, trf);
+        PEM_LAUNCHED();
+    }
+    pem_free(ctx, b_row_nnz);
+    *d_out = trf;
+    return PEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
+                    const int32_t* I, const int32_t* J, const double* V, int transpose,
+                    pem_tiled** out, pem_times* times)
+{
+    if (!ctx || !out) return PEM_ERR_ARG;
+    *out = nullptr;
+    if (rows < 0 || cols < 0 || nnz < 0) return ctx->fail(PEM_ERR_ARG, "negative size");
+    if (nnz > 0 && (!I || !J || !V)) return ctx->fail(PEM_ERR_ARG, "null COO array");
+    if (nnz >= (int64_t(1) << 32) - 1) return ctx->fail(PEM_ERR_LIMIT, "nnz must be below 2^32-1 (32-bit tile value offsets)");
+    PEM_CK(cudaSetDevice(ctx->device));
+    auto wall0 = std::chrono::high_resolution_clock::now();
+    if (transpose) { int32_t t = rows; rows = cols; cols = t; }
+
+    pem_tiled* T = new pem_tiled();
+    T->rows = rows; T->cols = cols; T->nnz = nnz;
+    T->tile_rows = (int32_t)(((int64_t)rows + PEM_TILE - 1) / PEM_TILE);
+    T->tile_cols = (int32_t)(((int64_t)cols + PEM_TILE - 1) / PEM_TILE);
+    auto fail = [&](int rc) { pem_tiled_free(ctx, T); return rc; };
+#define CV_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) return fail(rc_); } while (0)
+#define CV_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx->fail_cuda(e_, #call, __FILE__, __LINE__)); } while (0)
+
+    CV_TRY(pem_alloc(ctx, &T->tile_row_ptr, (size_t)T->tile_rows + 1));
+    CV_CK(cudaMemsetAsync(T->tile_row_ptr, 0, ((size_t)T->tile_rows + 1) * 4, ctx->stream));
+    float kernel_ms = 0.f;
+
+    if (nnz > 0) {
+        int cb = h_bits_for(T->tile_cols), rb = h_bits_for(T->tile_rows);
+        // stage the COO on the device if it came from the host (pinned or pageable)
+        int32_t *dI = nullptr, *dJ = nullptr;
+        double* dV = nullptr;
+        bool own = !is_device_ptr(I);
+        if (own) {
+            CV_TRY(pem_alloc(ctx, &dI, (size_t)nnz));
+            CV_TRY(pem_alloc(ctx, &dJ, (size_t)nnz));
+            CV_TRY(pem_alloc(ctx, &dV, (size_t)nnz));
+            CV_CK(cudaMemcpyAsync(dI, I, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CV_CK(cudaMemcpyAsync(dJ, J, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CV_CK(cudaMemcpyAsync(dV, V, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            dI = const_cast<int32_t*>(I); dJ = const_cast<int32_t*>(J); dV = const_cast<double*>(V);
+        }
+        uint64_t *keys = nullptr, *keys_sorted = nullptr;
+        CV_TRY(pem_alloc(ctx, &keys, (size_t)nnz));
+        CV_TRY(pem_alloc(ctx, &keys_sorted, (size_t)nnz));
+        CV_TRY(pem_alloc(ctx, &T->vals, (size_t)nnz));
+        CV_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
+
+        int grid = (int)std::min<int64_t>(pem_div_up(nnz, 256), (int64_t)ctx->sm_count * 32);
+        k_make_keys<<<grid, 256, 0, ctx->stream>>>(dI, dJ, nnz, rows, cols, transpose, cb, keys, ctx->d_scalars);
+        ++ctx->launches;
+        CV_CK(cudaGetLastError());
+
+        // one radix sort of (key, value) over the bits in use
+        size_t tmp_bytes = 0, tmp2 = 0;
+        CV_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, dV, T->vals, nnz, 0, 8 + cb + rb, ctx->stream));
+        uint32_t* start_tmp = nullptr;
+        CV_TRY(pem_alloc(ctx, &start_tmp, (size_t)nnz + 1));
+        cub::CountingInputIterator<uint32_t> iota(0);
+        HeadPred pred{keys_sorted};
+        int64_t* d_count = ctx->d_scalars + SC_COUNT;
+        CV_CK(cub::DeviceSelect::If(nullptr, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
+        char* tmp = nullptr;
+        CV_TRY(pem_alloc(ctx, &tmp, std::max(tmp_bytes, tmp2)));
+        CV_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, dV, T->vals, nnz, 0, 8 + cb + rb, ctx->stream));
+        CV_CK(cub::DeviceSelect::If(tmp, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
+        CV_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CV_CK(cudaStreamSynchronize(ctx->stream));
+        pem_free(ctx, tmp);
+        pem_free(ctx, keys);
+        if (own) { pem_free(ctx, dI); pem_free(ctx, dJ); pem_free(ctx, dV); }
+        if (ctx->h_scalars[SC_ERR] & 1) {
+            pem_free(ctx, keys_sorted); pem_free(ctx, start_tmp);
+            return fail(ctx->fail(PEM_ERR_RANGE, "COO coordinate outside the matrix"));
+        }
+        int64_t cnt = ctx->h_scalars[SC_COUNT];
+        if (cnt >= (int64_t(1) << 31) - 1) {
+            pem_free(ctx, keys_sorted); pem_free(ctx, start_tmp);
+            return fail(ctx->fail(PEM_ERR_LIMIT, "more than 2^31 tiles"));
+        }
+        T->tiles = (int32_t)cnt;
+        size_t n = (size_t)cnt;
+        CV_TRY(pem_alloc(ctx, &T->tile_nnz_ptr, n + 1));
+        CV_CK(cudaMemcpyAsync(T->tile_nnz_ptr, start_tmp, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        pem_free(ctx, start_tmp);
+        CV_TRY(pem_alloc(ctx, &T->masks, n * 16));
+        CV_TRY(pem_alloc(ctx, &T->masks_t, n * 16));
+        CV_TRY(pem_alloc(ctx, &T->row_ptr, n * 16));
+        CV_TRY(pem_alloc(ctx, &T->tile_col_idx, n));
+        CV_TRY(pem_alloc(ctx, &T->tile_row_idx, n));
+        CV_TRY(pem_alloc(ctx, &T->col_occ, n));
+        CV_TRY(pem_alloc(ctx, &T->row_occ, n));
+        CV_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_build_tiles<<<pem_div_up(cnt, 128), 128, 0, ctx->stream>>>(
+            keys_sorted, T->tile_nnz_ptr, (int)cnt, (uint32_t)nnz, cb, T->tile_rows, T->masks, T->masks_t,
+            T->row_ptr, T->tile_col_idx, T->tile_row_idx, T->tile_row_ptr, T->col_occ, T->row_occ, ctx->d_scalars);
+        ++ctx->launches;
+        CV_CK(cudaGetLastError());
+        CV_CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CV_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CV_CK(cudaStreamSynchronize(ctx->stream));
+        pem_free(ctx, keys_sorted);
+        if (ctx->h_scalars[SC_ERR] & 2) return fail(ctx->fail(PEM_ERR_DUPLICATE, "duplicate (i,j) in the COO input"));
+        cudaEventElapsedTime(&kernel_ms, ctx->ev[0], ctx->ev[1]);
+    } else {
+        CV_TRY(pem_alloc(ctx, &T->tile_nnz_ptr, 1));
+        CV_CK(cudaMemsetAsync(T->tile_nnz_ptr, 0, 4, ctx->stream));
+        CV_TRY(pem_alloc(ctx, &T->vals, 0)); CV_TRY(pem_alloc(ctx, &T->masks, 0)); CV_TRY(pem_alloc(ctx, &T->masks_t, 0));
+        CV_TRY(pem_alloc(ctx, &T->row_ptr, 0)); CV_TRY(pem_alloc(ctx, &T->tile_col_idx, 0));
+        CV_TRY(pem_alloc(ctx, &T->tile_row_idx, 0)); CV_TRY(pem_alloc(ctx, &T->col_occ, 0)); CV_TRY(pem_alloc(ctx, &T->row_occ, 0));
+        CV_CK(cudaStreamSynchronize(ctx->stream));
+    }
+#undef CV_TRY
+#undef CV_CK
+    if (times) {
+        auto wall1 = std::chrono::high_resolution_clock::now();
+        times->convert_kernel_ms = kernel_ms;
+        times->convert_total_ms = std::chrono::duration<double, std::milli>(wall1 - wall0).count();
+    }
+    *out = T;
+    return PEM_OK;
+}
+
+int pem_count_flop(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, uint64_t* flop)
+{
+    if (!ctx || !A || !B || !flop) return PEM_ERR_ARG;
+    if (A->cols != B->rows) return ctx->fail(PEM_ERR_ARG, "inner dimensions differ");
+    PEM_CK(cudaSetDevice(ctx->device));
+    unsigned long long* trf = nullptr;
+    PEM_TRY(tile_row_flops(ctx, A, B, &trf));
+    std::vector<unsigned long long> h((size_t)A->tile_rows);
+    if (A->tile_rows) PEM_CK(cudaMemcpyAsync(h.data(), trf, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PEM_CK(cudaStreamSynchronize(ctx->stream));
+    pem_free(ctx, trf);
+    uint64_t f = 0;
+    for (auto v : h) f += v;
+    *flop = f;
+    return PEM_OK;
+}
+
+int pem_partition_panels(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, int nparts, int32_t* bounds)
+{
+    if (!ctx || !A || !B || !bounds || nparts <= 0) return PEM_ERR_ARG;
+    if (A->cols != B->rows) return ctx->fail(PEM_ERR_ARG, "inner dimensions differ");
+    PEM_CK(cudaSetDevice(ctx->device));
+    unsigned long long* trf = nullptr;
+    PEM_TRY(tile_row_flops(ctx, A, B, &trf));
+    std::vector<unsigned long long> h((size_t)A->tile_rows);
+    if (A->tile_rows) PEM_CK(cudaMemcpyAsync(h.data(), trf, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PEM_CK(cudaStreamSynchronize(ctx->stream));
+    pem_free(ctx, trf);
+    unsigned long long total = 0;
+    for (auto v : h) total += v + 1;  // +1: rows without flop still cost a little and keep panels contiguous
+    bounds[0] = 0;
+    unsigned long long run = 0;
+    int part = 1;
+    for (int r = 0; r < A->tile_rows && part < nparts; ++r) {
+        run += h[(size_t)r] + 1;
+        // close panel `part` once it has reached its share of the prefix
+        while (part < nparts && run * (unsigned long long)nparts >= total * (unsigned long long)part) bounds[part++] = r + 1;
+    }
+    while (part <= nparts) bounds[part++] = A->tile_rows;
+    return PEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// Context, options, handle accessors and small shared device helpers of the C ABI.
+// Replaces the ad-hoc stream / RMM pool setup of the reference (spgemm.cu:757-758,808-817) with
+// one stream + one stream-ordered cudaMemPool_t whose release threshold is "never", so that
+// per-iteration cudaMallocAsync/cudaFreeAsync of the C-side buffers (spgemm.cu:1138-1295,
+// 1118-1131) are pool hits and leave the critical path.
+#include <cub/device/device_scan.cuh>
+
+#include <cstring>
+#include <new>
+
+#include "engine.cuh"
+
+extern "C" {
+
+int pem_ctx_create(pem_ctx** out, int device)
+{
+    if (!out) return PEM_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        (void)cudaGetLastError();
+        return PEM_ERR_NO_DEVICE;
+    }
+    pem_ctx* ctx = new (std::nothrow) pem_ctx();
+    if (!ctx) return PEM_ERR_ARG;
+    ctx->device = device;
+    auto bail = [&](cudaError_t e) {
+        fprintf(stderr, "pem_ctx_create: %s\n", cudaGetErrorString(e));
+        delete ctx;
+        return PEM_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if ((e = cudaMemPoolCreate(&ctx->pool, &props)) != cudaSuccess) return bail(e);
+    uint64_t never = UINT64_MAX;
+    if ((e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &never)) != cudaSuccess) return bail(e);
+    if ((e = cudaMallocHost((void**)&ctx->h_scalars, PEM_NSCALARS * sizeof(int64_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc((void**)&ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t))) != cudaSuccess) return bail(e);
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    *out = ctx;
+    return PEM_OK;
+}
+
+void pem_ctx_destroy(pem_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* pem_last_error(const pem_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx) return PEM_ERR_ARG;
+    switch (option) {
+        case PEM_OPT_KEEP_EMPTY_TILES: ctx->opt_keep_empty = value != 0; return PEM_OK;
+        case PEM_OPT_STEP1_PATH:
+            if (value < 0 || value > 2) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP1_PATH must be 0, 1 or 2");
+            ctx->opt_step1_path = (int)value;
+            return PEM_OK;
+    }
+    return ctx->fail(PEM_ERR_ARG, "unknown option");
+}
+
+void* pem_ctx_stream(pem_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int pem_ctx_sync(pem_ctx* ctx)
+{
+    if (!ctx) return PEM_ERR_ARG;
+    PEM_CK(cudaStreamSynchronize(ctx->stream));
+    return PEM_OK;
+}
+
+int64_t pem_ctx_launch_count(const pem_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t pem_ctx_pool_bytes(const pem_ctx* ctx)
+{
+    if (!ctx) return 0;
+    uint64_t v = 0;
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &v);
+    return (int64_t)v;
+}
+
+// ---- tiled accessors -----------------------------------------------------------------------
+int pem_tiled_info_get(const pem_tiled* t, pem_tiled_info* info)
+{
+    if (!t || !info) return PEM_ERR_ARG;
+    info->rows = t->rows; info->cols = t->cols; info->nnz = t->nnz;
+    info->tile_rows = t->tile_rows; info->tile_cols = t->tile_cols; info->tiles = t->tiles;
+    return PEM_OK;
+}
+
+static const void* tiled_array(const pem_tiled* t, int which, size_t* bytes)
+{
+    size_t n = (size_t)t->tiles;
+    switch (which) {
+        case PEM_T_VALS: *bytes = (size_t)t->nnz * 8; return t->vals;
+        case PEM_T_TILE_NNZ_PTR: *bytes = (n + 1) * 4; return t->tile_nnz_ptr;
+        case PEM_T_MASKS: *bytes = n * 32; return t->masks;
+        case PEM_T_ROW_PTR: *bytes = n * 16; return t->row_ptr;
+        case PEM_T_MASKS_T: *bytes = n * 32; return t->masks_t;
+        case PEM_T_TILE_ROW_PTR: *bytes = ((size_t)t->tile_rows + 1) * 4; return t->tile_row_ptr;
+        case PEM_T_TILE_COL_IDX: *bytes = n * 4; return t->tile_col_idx;
+        case PEM_T_TILE_ROW_IDX: *bytes = n * 4; return t->tile_row_idx;
+        case PEM_T_COL_OCC: *bytes = n * 2; return t->col_occ;
+        case PEM_T_ROW_OCC: *bytes = n * 2; return t->row_occ;
+    }
+    *bytes = 0;
+    return nullptr;
+}
+
+const void* pem_tiled_device_ptr(const pem_tiled* t, int which)
+{
+    size_t b;
+    return t ? tiled_array(t, which, &b) : nullptr;
+}
+
+int pem_tiled_get(pem_ctx* ctx, const pem_tiled* t, int which, void* host_dst, size_t bytes)
+{
+    if (!ctx || !t || !host_dst) return PEM_ERR_ARG;
+    size_t have = 0;
+    const void* src = tiled_array(t, which, &have);
+    if (!src && have == 0 && which > PEM_T_ROW_OCC) return ctx->fail(PEM_ERR_ARG, "unknown tiled array");
+    if (bytes != have) return ctx->fail(PEM_ERR_ARG, "pem_tiled_get: size mismatch");
+    if (bytes == 0) return PEM_OK;
+    PEM_CK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PEM_CK(cudaStreamSynchronize(ctx->stream));
+    return PEM_OK;
+}
+
+void pem_tiled_free(pem_ctx* ctx, pem_tiled* t)
+{
+    if (!ctx || !t) return;
+    pem_free(ctx, t->vals); pem_free(ctx, t->tile_nnz_ptr); pem_free(ctx, t->masks);
+    pem_free(ctx, t->masks_t); pem_free(ctx, t->row_ptr); pem_free(ctx, t->tile_row_ptr);
+    pem_free(ctx, t->tile_col_idx); pem_free(ctx, t->tile_row_idx); pem_free(ctx, t->col_occ);
+    pem_free(ctx, t->row_occ);
+    delete t;
+}
+
+// ---- result accessors ----------------------------------------------------------------------
+int pem_result_info_get(const pem_result* C, pem_result_info* info)
+{
+    if (!C || !info) return PEM_ERR_ARG;
+    info->tile_row_begin = C->rb; info->tile_row_end = C->re;
+    info->rows = C->rows; info->cols = C->cols;
+    info->tiles = C->tiles; info->pairs = C->pairs; info->nnz = C->nnz;
+    info->tile_products = C->tile_products;
+    return PEM_OK;
+}
+
+static const void* result_array(const pem_result* C, int which, size_t* bytes)
+{
+    size_t n = (size_t)C->tiles;
+    switch (which) {
+        case PEM_R_ROW_PTR: *bytes = ((size_t)(C->re - C->rb) + 1) * 8; return C->row_ptr;
+        case PEM_R_TILE_ROW: *bytes = n * 4; return C->tile_row;
+        case PEM_R_TILE_COL: *bytes = n * 4; return C->tile_col;
+        case PEM_R_PAIR_PTR: *bytes = (n + 1) * 8; return C->pair_ptr;
+        case PEM_R_PAIRS_A: *bytes = (size_t)C->pairs * 4; return C->pairs_a;
+        case PEM_R_PAIRS_B: *bytes = (size_t)C->pairs * 4; return C->pairs_b;
+        case PEM_R_MASKS: *bytes = C->stage >= 2 ? n * 32 : 0; return C->masks;
+        case PEM_R_TILE_NNZ_PTR: *bytes = C->stage >= 2 ? (n + 1) * 8 : 0; return C->tile_nnz_ptr;
+        case PEM_R_ROW_COL_IDX: *bytes = C->stage >= 2 ? (size_t)C->nnz : 0; return C->row_col_idx;
+        case PEM_R_VALS: *bytes = C->stage >= 3 ? (size_t)C->nnz * 8 : 0; return C->vals;
+    }
+    *bytes = 0;
+    return nullptr;
+}
+
+const void* pem_result_device_ptr(const pem_result* C, int which)
+{
+    size_t b;
+    return C ? result_array(C, which, &b) : nullptr;
+}
+
+int pem_result_get(pem_ctx* ctx, const pem_result* C, int which, void* host_dst, size_t bytes)
+{
+    if (!ctx || !C || !host_dst) return PEM_ERR_ARG;
+    size_t have = 0;
+    const void* src = result_array(C, which, &have);
+    if (bytes != have) return ctx->fail(PEM_ERR_ARG, "pem_result_get: size mismatch (or stage not run yet)");
+    if (bytes == 0) return PEM_OK;
+    PEM_CK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PEM_CK(cudaStreamSynchronize(ctx->stream));
+    return PEM_OK;
+}
+
+void pem_result_free(pem_ctx* ctx, pem_result* C)
+{
+    if (!ctx || !C) return;
+    pem_free(ctx, C->row_ptr); pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col);
+    pem_free(ctx, C->pair_ptr); pem_free(ctx, C->pairs_a); pem_free(ctx, C->pairs_b);
+    pem_free(ctx, C->masks); pem_free(ctx, C->tile_nnz_ptr); pem_free(ctx, C->row_col_idx);
+    pem_free(ctx, C->vals); pem_free(ctx, C->blk_tile);
+    delete C;
+}
+
+}  // extern "C"
+
+// In-place exclusive prefix sum over n int64 values (CUB device scan as a building block; the
+// reference uses thrust::exclusive_scan at the same places, spgemm.cu:1168,1242,1288).
+int pem_scan_exclusive_i64(pem_ctx* ctx, int64_t* d, int64_t n)
+{
+    if (n <= 0) return PEM_OK;
+    size_t tmp_bytes = 0;
+    PEM_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d, d, n, ctx->stream));
+    char* tmp = nullptr;
+    PEM_TRY(pem_alloc(ctx, &tmp, tmp_bytes));
+    PEM_CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d, d, n, ctx->stream));
+    pem_free(ctx, tmp);
+    return PEM_OK;
+}

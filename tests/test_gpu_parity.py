@@ -1,0 +1,197 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA engine, called through the C ABI,
+against the host oracle on identical seeded inputs.  Structure and indices must be bit-exact;
+values are compared bit-exact as well (the engine keeps the oracle's ascending-k fma order),
+with the north-star tolerance 1e-12 as the stated bound for floating point."""
+import numpy as np
+import pytest
+
+import pem_spgemm_b200 as pem
+from oracle import host, tiles
+from pem_spgemm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12  # north_star tolerance for fp64 values
+
+
+def _assert_same_C(Cres, Coracle, exact=True):
+    r, c, v = Cres.to_coo()
+    ro, co, vo = Coracle.to_coo()
+    assert r.size == ro.size
+    assert np.array_equal(r, ro) and np.array_equal(c, co)          # structure: bit-exact
+    np.testing.assert_allclose(v, vo, rtol=RTOL, atol=0)            # the stated tolerance
+    if exact:
+        assert np.array_equal(v, vo)                                 # same fma order => same bits
+
+
+def _check_tiled(T, O):
+    i = T.info
+    assert (i.rows, i.cols, i.tile_rows, i.tile_cols, i.tiles) == (O.rows, O.cols, O.tile_rows, O.tile_cols, O.cnt)
+    assert np.array_equal(T.array("tile_nnz_ptr").astype(np.int64), O.tile_nnz_ptr)
+    assert np.array_equal(T.array("vals"), O.vals)
+    assert np.array_equal(T.array("masks").reshape(-1, 16), O.masks)
+    assert np.array_equal(T.array("masks_t").reshape(-1, 16), O.masks_t)
+    assert np.array_equal(T.array("row_ptr").reshape(-1, 16), O.row_ptr)
+    assert np.array_equal(T.array("tile_row_ptr"), O.tile_row_ptr)
+    assert np.array_equal(T.array("tile_col_idx"), O.tile_col)
+    assert np.array_equal(T.array("tile_row_idx"), O.tile_row)
+    z = np.zeros(0, np.uint16)
+    assert np.array_equal(T.array("col_occ"), np.bitwise_or.reduce(O.masks, axis=1) if O.cnt else z)
+    assert np.array_equal(T.array("row_occ"), np.bitwise_or.reduce(O.masks_t, axis=1) if O.cnt else z)
+
+
+SHAPES = [((50, 70), 400, 11), ((16, 16), 256, 4), ((1, 1), 1, 1), ((333, 333), 5000, 2),
+          ((17, 4000), 3000, 3), ((4000, 17), 3000, 5), ((1000, 1000), 1, 6)]
+
+
+@pytest.mark.parametrize("shape,nnz,seed", SHAPES)
+@pytest.mark.parametrize("transpose", [False, True])
+def test_conversion_matches_tile_oracle(engine, shape, nnz, seed, transpose):
+    rows, cols, I, J, V = synth.random_sparse(*shape, nnz, seed=seed)
+    T = engine.convert_coo(rows, cols, I, J, V, transpose=transpose)
+    _check_tiled(T, tiles.tile_format(rows, cols, I, J, V, transpose=transpose))
+    T.free()
+
+
+def test_conversion_dense_tile_and_empty(engine):
+    I, J = np.divmod(np.arange(256, dtype=np.int32), 16)
+    V = np.arange(256, dtype=np.float64)
+    T = engine.convert_coo(16, 16, I, J, V)
+    assert T.array("row_ptr")[-1] == 240 and np.all(T.array("masks") == 0xFFFF)
+    T.free()
+    z = np.zeros(0, np.int32)
+    E = engine.convert_coo(40, 40, z, z, np.zeros(0))
+    assert E.info.tiles == 0 and np.all(E.array("tile_row_ptr") == 0)
+    C = engine.spgemm(E, E)
+    assert C.info.nnz == 0 and C.info.tiles == 0
+    assert C.to_coo()[0].size == 0
+    C.free(); E.free()
+
+
+def test_conversion_input_errors(engine):
+    I = np.array([0, 0], np.int32); J = np.array([1, 1], np.int32)
+    with pytest.raises(pem.PemError) as e:
+        engine.convert_coo(4, 4, I, J, np.ones(2))
+    assert e.value.code == -4
+    with pytest.raises(pem.PemError) as e:
+        engine.convert_coo(4, 4, np.array([4], np.int32), np.array([0], np.int32), np.ones(1))
+    assert e.value.code == -3
+    rows, cols, I, J, V = synth.random_sparse(10, 30, 50, seed=1)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    with pytest.raises(pem.PemError) as e:       # rectangular A*A is rejected (spgemm.cu:782-786)
+        engine.spgemm(A, A)
+    assert e.value.code == -2
+    A.free()
+
+
+@pytest.mark.parametrize("keep_empty", [1, 0])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_steps_match_tile_oracle(engine, k, keep_empty):
+    """Step-by-step parity of C' structure, ordered pair lists, C masks and per-tile nnz."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep_empty)
+    try:
+        A = engine.convert_coo(rows, cols, I, J, V)
+        B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+        OA = tiles.tile_format(rows, cols, I, J, V)
+        OB = tiles.tile_format(rows, cols, I, J, V, transpose=tb)
+        P = tiles.tiled_product(OA, OB, keep_empty=bool(keep_empty))
+        C = engine.step1(A, B)
+        info = C.info
+        assert (info.tiles, info.pairs) == (P.c_tile_col.size, P.pairs_a.size)
+        assert np.array_equal(C.array("row_ptr"), P.c_row_ptr)
+        assert np.array_equal(C.array("tile_row"), P.c_tile_row)
+        assert np.array_equal(C.array("tile_col"), P.c_tile_col)
+        assert np.array_equal(C.array("pair_ptr"), P.pair_ptr)
+        assert np.array_equal(C.array("pairs_a"), P.pairs_a)
+        assert np.array_equal(C.array("pairs_b"), P.pairs_b)
+        engine.step2(A, B, C)
+        assert np.array_equal(C.array("masks").reshape(-1, 16), P.c_masks)
+        assert np.array_equal(C.array("tile_nnz_ptr"), P.c_tile_nnz_ptr)
+        # rowColIdx: (r<<4)|c of every set mask bit, tile by tile, row-major (spgemm.cu:582-587)
+        t, r = np.nonzero(P.c_masks)
+        bits = (P.c_masks[t, r].astype(np.int64)[:, None] >> np.arange(16)) & 1
+        idx, cc = np.nonzero(bits)
+        want = ((r[idx] << 4) | cc).astype(np.uint8)
+        assert np.array_equal(C.array("row_col_idx"), want)
+        engine.step3(A, B, C)
+        _, _, Co = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+        _assert_same_C(C, Co)
+        C.free(); A.free(); B.free()
+    finally:
+        engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+
+
+@pytest.mark.parametrize("shape,nnz,seed", SHAPES)
+def test_spgemm_aat_random(engine, shape, nnz, seed):
+    rows, cols, I, J, V = synth.random_sparse(*shape, nnz, seed=seed)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=True)
+    C = engine.spgemm(A, B)
+    oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, True)
+    _assert_same_C(C, oC)
+    assert engine.count_flop(A, B) == host.flop(oA, oB)
+    s, a = C.checksum()
+    np.testing.assert_allclose([s, a], [oC.val.sum(), np.abs(oC.val).sum()], rtol=1e-9, atol=1e-9)
+    C.free(); A.free(); B.free()
+
+
+def test_structural_zero_kept(engine):
+    I = np.array([0, 0, 1, 1], np.int32); J = np.array([0, 1, 0, 1], np.int32)
+    A = engine.convert_coo(2, 2, I, J, np.array([1.0, 1.0, 1.0, -1.0]))
+    C = engine.spgemm(A, A)
+    r, c, v = C.to_coo()
+    assert list(v) == [2.0, 0.0, 0.0, 2.0]
+    C.free(); A.free()
+
+
+def test_config1_full_known_answers(engine):
+    """Config 1 at full size against the pinned numbers of SURVEY.md section 8c."""
+    rows, cols, I, J, V = synth.laplacian2d(256)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    assert A.info.tiles == 19_936 and A.info.tile_rows == 4_096
+    assert engine.count_flop(A, A) == 1_629_192
+    engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 1)
+    C = engine.spgemm(A, A)
+    engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+    assert (C.info.tiles, C.info.pairs, C.info.nnz) == (50_532, 97_512, 846_852)
+    C.free()
+    C = engine.spgemm(A, A)
+    assert (C.info.tiles, C.info.nnz) == (43_364, 846_852)
+    assert C.checksum() == (1032.0, 4_178_952.0)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, False)
+    _assert_same_C(C, oC)
+    C.free(); A.free()
+
+
+@pytest.mark.parametrize("k,nparts", [(2, 3), (4, 8), (3, 2)])
+def test_panels_concatenate_to_full_result(engine, k, nparts):
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+    bounds = engine.partition_panels(A, B, nparts)
+    assert bounds[0] == 0 and bounds[-1] == A.info.tile_rows and np.all(np.diff(bounds) >= 0)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    parts = []
+    for p in range(nparts):
+        C = engine.spgemm(A, B, panel=(bounds[p], bounds[p + 1]))
+        parts.append(C.to_coo()); C.free()
+    r = np.concatenate([x[0] for x in parts]); c = np.concatenate([x[1] for x in parts])
+    v = np.concatenate([x[2] for x in parts])
+    ro, co, vo = oC.to_coo()
+    assert np.array_equal(r, ro) and np.array_equal(c, co) and np.array_equal(v, vo)
+    A.free(); B.free()
+
+
+def test_device_pointer_input_and_pool_reuse(engine):
+    import torch
+    rows, cols, I, J, V = synth.random_sparse(2000, 2000, 30000, seed=8)
+    dI = torch.from_numpy(I).cuda(); dJ = torch.from_numpy(J).cuda(); dV = torch.from_numpy(V).cuda()
+    torch.cuda.synchronize()
+    A = engine.convert_coo(rows, cols, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), nnz=I.size)
+    _check_tiled(A, tiles.tile_format(rows, cols, I, J, V))
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, False)
+    for _ in range(3):                      # repeated products recycle pool memory
+        C = engine.spgemm(A, A)
+        _assert_same_C(C, oC)
+        C.free()
+    A.free()

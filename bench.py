@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the SpGEMM hot path: SpGEMM GFLOP/s = 2*flop / time for C = A^2 (or A*A^T).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--impl ours|reference]
+
+One "step" is one full SpGEMM (steps 1-3 including allocation, i.e. one iteration of the
+reference's timed loop, /root/reference/spgemm.cu:1133-1357) on operands already resident in HBM
+in tiled form.  At N > 1 (torchrun, one process per GPU) A's tile rows are split into N
+flop-balanced panels, B is replicated, each rank multiplies its panel, and the per-shard
+{nnz, tiles, pairs} are all-gathered over NCCL (the only exchange on this path); the time is the
+max over ranks and the value is the whole job's 2*flop / time ("strong" scaling: same matrix at
+every N).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIG_TEXT = {
+    1: "config1: A^2, 2-D 5-point Laplacian 256x256 grid (n=65,536)",
+    2: "config2: A^2, synthetic webbase-1M-shaped power-law matrix (n=1,000,005, nnz=3,091,482)",
+    3: "config3: A*A^T, synthetic LP-shaped 100,000 x 1,000,000, 100 nnz/row",
+    4: "config4: A^2, synthetic cage15-shaped 19-point stencil 172x173x173 (n=5,147,788)",
+    5: "config5: conversion + A^2, synthetic R-MAT (see synth.config(5))",
+}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(a_rows, a_nnz, b_rows, b_nnz, c_rows, c_nnz):
+    """CSR-equivalent compulsory traffic, int32 indices + fp64 values."""
+    return 12 * a_nnz + 4 * (a_rows + 1) + 12 * b_nnz + 4 * (b_rows + 1) + 12 * c_nnz + 4 * (c_rows + 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_workload(k):
+    from pem_spgemm_b200 import synth
+    name, tb, (rows, cols, I, J, V) = synth.config(k)
+    return name, tb, rows, cols, np.ascontiguousarray(I), np.ascontiguousarray(J), np.ascontiguousarray(V)
+
+
+def oracle_cpu(rows, cols, I, J, V, tb):
+    """The host oracle timed on this box's cores (reported baseline, not the target)."""
+    from oracle import host   # cpu_baseline leg: one of the places allowed to run oracle/
+    A = host.coo_to_csr(rows, cols, I, J, V)
+    B = host.transpose(A) if tb else A
+    flop = host.flop(A, B)
+    tm = {}
+    host.spgemm(A, B, tm)
+    return flop, tm["seconds"], tm["threads"]
+
+
+def run_reference(args, rank):
+    """--impl reference: the UNMODIFIED reference (oracle/_ref/pemspgemm_ref = /root/reference's
+    spgemm.cu compiled for sm_100 against shim headers) through its own CLI on one B200; if that
+    binary is missing or fails on this input, the host oracle port on the box's cores."""
+    if rank != 0:
+        return
+    import pem_spgemm_b200 as pem
+    name, tb, rows, cols, I, J, V = load_workload(args.config)
+    line = {"impl": "reference", "metric": "spgemm_gflops", "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": CONFIG_TEXT[args.config]}}
+    ref = os.path.join(ROOT, "oracle", "_ref", "pemspgemm_ref")
+    done = False
+    if os.path.exists(ref):
+        work = f"/tmp/pem_ref_{os.getpid()}"
+        os.makedirs(work, exist_ok=True)
+        mtx = os.path.join(work, f"{name}.mtx")
+        pem.mtx_write(mtx, rows, cols, I, J, V)
+        cmd = [ref, mtx, "0"] + (["1"] if tb else [])
+        try:
+            t0 = time.time()
+            out = subprocess.run(cmd, cwd=work, capture_output=True, text=True, timeout=1500)
+            wall = time.time() - t0
+            row = open(os.path.join(work, "pemspgemm_benchmark_result.csv")).read().strip().splitlines()[-1].split(",")
+            flop, c_nnz, t_ms, gf = int(row[1]), int(row[2]), float(row[10]), float(row[13])
+            if out.returncode == 0 and t_ms > 0 and c_nnz > 0:
+                line.update({"value": gf, "ms_per_step": t_ms, "steps": 10, "warmup": 1,
+                             "reference_csv": {"flop": flop, "C_nnz": c_nnz, "step1_ms": float(row[7]),
+                                               "step2_ms": float(row[8]), "step3_ms": float(row[9]),
+                                               "kernel_ms": float(row[11]), "malloc_ms": float(row[12])},
+                             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": 0, "kind": "reference",
+                                              "sample": "reference CUDA source rebuilt for sm_100, its own CLI: "
+                                                        "1 warm-up + 10 timed iterations on 1 B200 (it has no CPU path); "
+                                                        f"whole process {wall:.1f}s"},
+                             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+                done = True
+            else:
+                line["reference_failure"] = f"rc={out.returncode} time_ms={t_ms} C_nnz={c_nnz}: {out.stderr[-300:]}"
+        except Exception as e:  # crash, timeout, no CSV
+            line["reference_failure"] = f"{type(e).__name__}: {e}"[:400]
+    else:
+        line["reference_failure"] = "oracle/_ref/pemspgemm_ref not built"
+    if not done:
+        flop, secs, thr = oracle_cpu(rows, cols, I, J, V, tb)
+        gf = 2.0 * flop / secs / 1e9
+        line.update({"value": gf, "ms_per_step": secs * 1e3, "steps": 1, "warmup": 0,
+                     "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": thr, "kind": "port",
+                                      "sample": "full workload, 1 run of the OpenMP Gustavson oracle"},
+                     "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--keep-empty", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pem_spgemm_b200 as pem
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name, tb, rows, cols, I, J, V = load_workload(args.config)
+    ctx = pem.Context(local_rank)
+    ctx.set_option(pem.OPT_KEEP_EMPTY_TILES, args.keep_empty)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    # operands resident in HBM before the timed region
+    tI = torch.from_numpy(I).pin_memory(); tJ = torch.from_numpy(J).pin_memory(); tV = torch.from_numpy(V).pin_memory()
+    A = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
+    B = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A
+    flop = ctx.count_flop(A, B)
+    bounds = ctx.partition_panels(A, B, world)
+    panel = (int(bounds[rank]), int(bounds[rank + 1]))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def one_step(times=None):
+        C = ctx.spgemm(A, B, times=times, panel=panel)
+        info = C.info
+        shard = torch.tensor([info.nnz, info.tiles, info.pairs], dtype=torch.int64, device="cuda")
+        if world > 1:                       # the path's only exchange: per-shard sizes -> global offsets
+            allsz = torch.empty(world * 3, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allsz, shard)
+            shard = allsz.view(world, 3).sum(0)
+        C.free()
+        return shard
+
+    for _ in range(args.warmup):
+        sizes = one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    step_ms, s1, s2, s3 = [], [], [], []
+    for _ in range(args.steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t = pem.Times()
+        e0.record(stream)
+        sizes = one_step(t)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        step_ms.append(float(ms.item()))
+        s1.append(t.step1_ms); s2.append(t.step2_ms); s3.append(t.step3_ms)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    c_nnz, c_tiles, c_pairs = (int(x) for x in sizes.tolist())
+    ms_per_step = float(np.mean(step_ms))
+    value = 2.0 * flop / (ms_per_step * 1e6)
+
+    # ---- end to end through the C ABI with HOST buffers: H2D of the COO, conversion, SpGEMM,
+    #      D2H of the result summary (nnz/tiles + device-reduced checksum), every step
+    e2e_ms = []
+    for _ in range(max(3, min(args.steps, 5))):
+        barrier()
+        t0 = time.perf_counter()
+        A2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
+        B2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A2
+        C2 = ctx.spgemm(A2, B2, panel=panel)
+        chk = C2.checksum()
+        ctx.sync()
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e_ms.append(float(ms.item()))
+        C2.free()
+        if B2 is not A2:
+            B2.free()
+        A2.free()
+    e2e_t = float(np.mean(e2e_ms[1:])) if len(e2e_ms) > 1 else e2e_ms[0]
+    h2d = int(I.nbytes + J.nbytes + V.nbytes) * (2 if tb else 1)
+    d2h = 2 * 1024 * 2 * 8 + 3 * 8 * 16     # checksum partials + the size read-backs of one step
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        ai = A.info; bi = B.info
+        bytes_alg = algorithmic_bytes(ai.rows, ai.nnz, bi.rows, bi.nnz, ai.rows, c_nnz)
+        t3 = float(np.mean(s3))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(f"config{args.config}")
+        except Exception:
+            pass
+        line = {
+            "metric": "spgemm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": CONFIG_TEXT[args.config], "product": "A*A^T" if tb else "A^2",
+                       "flop": flop, "nnz_A": int(ai.nnz), "nnz_C": c_nnz, "C_tiles": c_tiles, "tile_pairs": c_pairs,
+                       "parallelism": f"tile-row panels x{world}, B replicated",
+                       "l2": "no flush: each step streams > 1 GB (C + C' metadata), far above the 126 MB L2",
+                       "keep_empty_tiles": args.keep_empty},
+            "step_ms": {"step1": float(np.mean(s1)), "step2": float(np.mean(s2)), "step3": t3},
+            "roofline": {"bound": "hbm", "kernel": "k_step3_numeric", "achieved": bytes_alg / (t3 * 1e6) if t3 > 0 else None,
+                         "peak": peak, "unit": "GB/s", "frac": (bytes_alg / (t3 * 1e6) / peak) if t3 > 0 else None,
+                         "traffic": traffic, "algorithmic_bytes": bytes_alg, "peak_source": peak_src,
+                         "whole_spgemm_frac": bytes_alg / (ms_per_step * 1e6) / peak},
+            "e2e": {"value": 2.0 * flop / (e2e_t * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_t,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "host COO (pinned) -> pem_convert_coo -> pem_spgemm -> checksum/sizes read back"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            f2, secs, thr = oracle_cpu(rows, cols, I, J, V, tb)
+            assert f2 == flop, "engine and oracle disagree on flop"
+            line["cpu_baseline"] = {"value": 2.0 * flop / secs / 1e9, "unit": "GFLOP/s", "cores": thr, "kind": "port",
+                                    "sample": "full workload, 1 run of the OpenMP Gustavson oracle (symbolic + numeric)"}
+        print(json.dumps(line), flush=True)
+    if B is not A:
+        B.free()
+    A.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

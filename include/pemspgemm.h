@@ -53,7 +53,11 @@ typedef enum pem_option {
     /* step-1 accumulator choice per tile row: 0 = automatic (default), 1 = force the bitmap
      * (SPA) path, 2 = force the hash path.  Replaces the reference's global switch
      * `B_tileCols > 512*32` (spgemm.cu:1142). */
-    PEM_OPT_STEP1_PATH = 2
+    PEM_OPT_STEP1_PATH = 2,
+    /* thread mapping of steps 2 and 3: 0 (default) = one thread per C' tile / per C nonzero
+     * ("entry-owner", dense lane packing), 1 = sixteen lanes per C' tile, lane = tile row
+     * ("row-owner", accumulators in shared memory).  Results are bit-identical. */
+    PEM_OPT_OWNER = 3
 } pem_option;
 
 /* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are

@@ -25,6 +25,7 @@ STATUS = {0: "PEM_OK", -1: "PEM_ERR_CUDA", -2: "PEM_ERR_ARG", -3: "PEM_ERR_RANGE
           -4: "PEM_ERR_DUPLICATE", -5: "PEM_ERR_LIMIT", -6: "PEM_ERR_NO_DEVICE", -7: "PEM_ERR_IO"}
 OPT_KEEP_EMPTY_TILES = 1
 OPT_STEP1_PATH = 2
+OPT_OWNER = 3
 
 # pem_tiled_array / pem_result_array -> (index, dtype)
 T_ARRAYS = {

@@ -10,6 +10,54 @@
 
 #include "engine.cuh"
 
+// ---- caching allocator -----------------------------------------------------------------------
+// Replaces the reference's per-iteration cudaMallocAsync + 11 blocking cudaFree (spgemm.cu:1118-1131,
+// 1138-1295; its malloc_time).  Blocks come from the context's cudaMemPool_t once and are then
+// recycled by size: a block serves a request of up to its own size and no less than 3/4 of it.
+int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
+{
+    bytes = (bytes + 511) & ~(size_t)511;
+    auto it = ctx->free_blocks.lower_bound(bytes);
+    if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 4) {
+        *p = it->second;
+        ctx->live_blocks[*p] = it->first;
+        ctx->cached_bytes -= it->first;
+        ctx->free_blocks.erase(it);
+        return PEM_OK;
+    }
+    if (ctx->cached_bytes > ctx->cache_limit) pem_cache_release(ctx);
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
+        (void)cudaGetLastError();
+        pem_cache_release(ctx);
+        e = cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+    }
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
+    ctx->live_blocks[*p] = bytes;
+    return PEM_OK;
+}
+
+void pem_free_bytes(pem_ctx* ctx, void* p)
+{
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) {     // not ours (should not happen): plain stream-ordered free
+        cudaFreeAsync(p, ctx->stream);
+        return;
+    }
+    ctx->free_blocks.emplace(it->second, p);
+    ctx->cached_bytes += it->second;
+    ctx->live_blocks.erase(it);
+}
+
+void pem_cache_release(pem_ctx* ctx)
+{
+    for (auto& kv : ctx->free_blocks) cudaFreeAsync(kv.second, ctx->stream);
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPoolTrimTo(ctx->pool, 0);
+}
+
 extern "C" {
 
 int pem_ctx_create(pem_ctx** out, int device)
@@ -46,6 +94,8 @@ int pem_ctx_create(pem_ctx** out, int device)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit = total_b / 4;
     *out = ctx;
     return PEM_OK;
 }
@@ -54,6 +104,9 @@ void pem_ctx_destroy(pem_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    pem_cache_release(ctx);
+    for (auto& kv : ctx->live_blocks) cudaFreeAsync(kv.first, ctx->stream);   // handles the caller leaked
     cudaStreamSynchronize(ctx->stream);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -74,6 +127,10 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
         case PEM_OPT_STEP1_PATH:
             if (value < 0 || value > 2) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP1_PATH must be 0, 1 or 2");
             ctx->opt_step1_path = (int)value;
+            return PEM_OK;
+        case PEM_OPT_OWNER:
+            if (value < 0 || value > 1) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0 or 1");
+            ctx->opt_owner = (int)value;
             return PEM_OK;
     }
     return ctx->fail(PEM_ERR_ARG, "unknown option");
@@ -174,8 +231,8 @@ static const void* result_array(const pem_result* C, int which, size_t* bytes)
         case PEM_R_TILE_ROW: *bytes = n * 4; return C->tile_row;
         case PEM_R_TILE_COL: *bytes = n * 4; return C->tile_col;
         case PEM_R_PAIR_PTR: *bytes = (n + 1) * 8; return C->pair_ptr;
-        case PEM_R_PAIRS_A: *bytes = (size_t)C->pairs * 4; return C->pairs_a;
-        case PEM_R_PAIRS_B: *bytes = (size_t)C->pairs * 4; return C->pairs_b;
+        case PEM_R_PAIRS_A: *bytes = (size_t)C->pairs * 4; return C->pair_list;                   // stride 8 bytes
+        case PEM_R_PAIRS_B: *bytes = (size_t)C->pairs * 4; return (const int32_t*)C->pair_list + 1;   // stride 8 bytes
         case PEM_R_MASKS: *bytes = C->stage >= 2 ? n * 32 : 0; return C->masks;
         case PEM_R_TILE_NNZ_PTR: *bytes = C->stage >= 2 ? (n + 1) * 8 : 0; return C->tile_nnz_ptr;
         case PEM_R_ROW_COL_IDX: *bytes = C->stage >= 2 ? (size_t)C->nnz : 0; return C->row_col_idx;
@@ -194,11 +251,15 @@ const void* pem_result_device_ptr(const pem_result* C, int which)
 int pem_result_get(pem_ctx* ctx, const pem_result* C, int which, void* host_dst, size_t bytes)
 {
     if (!ctx || !C || !host_dst) return PEM_ERR_ARG;
+    if (which == PEM_R_ROW_COL_IDX && C->stage >= 2) PEM_TRY(pem_result_make_rowcolidx(ctx, const_cast<pem_result*>(C)));
     size_t have = 0;
     const void* src = result_array(C, which, &have);
     if (bytes != have) return ctx->fail(PEM_ERR_ARG, "pem_result_get: size mismatch (or stage not run yet)");
     if (bytes == 0) return PEM_OK;
-    PEM_CK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (which == PEM_R_PAIRS_A || which == PEM_R_PAIRS_B)   // stored interleaved as int2 on the device
+        PEM_CK(cudaMemcpy2DAsync(host_dst, 4, src, 8, 4, (size_t)C->pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+        PEM_CK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     return PEM_OK;
 }
@@ -207,9 +268,9 @@ void pem_result_free(pem_ctx* ctx, pem_result* C)
 {
     if (!ctx || !C) return;
     pem_free(ctx, C->row_ptr); pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col);
-    pem_free(ctx, C->pair_ptr); pem_free(ctx, C->pairs_a); pem_free(ctx, C->pairs_b);
+    pem_free(ctx, C->pair_ptr); pem_free(ctx, C->pair_list); pem_free(ctx, C->pair_hit); pem_free(ctx, C->blk_tile);
     pem_free(ctx, C->masks); pem_free(ctx, C->tile_nnz_ptr); pem_free(ctx, C->row_col_idx);
-    pem_free(ctx, C->vals); pem_free(ctx, C->blk_tile);
+    pem_free(ctx, C->vals);
     delete C;
 }
 

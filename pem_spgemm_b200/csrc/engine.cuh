@@ -4,7 +4,9 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <unordered_map>
 
 #include "pemspgemm.h"
 
@@ -21,11 +23,17 @@ struct pem_ctx {
     int64_t launches = 0;        // kernels of this library launched on the stream
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
+    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = entry-owner steps 2/3 (default), 1 = row-owner
     int sm_count = 148;
     int smem_optin = 227 * 1024; // max dynamic shared memory per block
     int64_t* h_scalars = nullptr; // pinned, PEM_NSCALARS entries: size read-backs
     int64_t* d_scalars = nullptr; // device mirror the kernels reduce into
     cudaEvent_t ev[PEM_NEVENTS] = {};
+    // caching layer over the pool: freed blocks are kept by size and handed out again in stream
+    // order (all work of a context is on one stream), so a repeated SpGEMM allocates nothing
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live_blocks;
+    size_t cached_bytes = 0, cache_limit = (size_t)32 << 30;
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int fail_cuda(cudaError_t e, const char* what, const char* file, int line)
@@ -58,18 +66,20 @@ struct pem_ctx {
         if (rc__ != PEM_OK) return rc__; \
     } while (0)
 
-// stream-ordered allocation from the context's pool (never returns a null pointer for n == 0)
+// stream-ordered allocation from the context's pool through the caching layer
+// (never returns a null pointer for n == 0)
+int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes);
+void pem_free_bytes(pem_ctx* ctx, void* p);
+void pem_cache_release(pem_ctx* ctx);
 template <class T>
 static inline int pem_alloc(pem_ctx* ctx, T** p, size_t n)
 {
-    size_t bytes = (n ? n : 1) * sizeof(T);
-    PEM_CK(cudaMallocFromPoolAsync((void**)p, bytes, ctx->pool, ctx->stream));
-    return PEM_OK;
+    return pem_alloc_bytes(ctx, (void**)p, (n ? n : 1) * sizeof(T));
 }
 template <class T>
 static inline void pem_free(pem_ctx* ctx, T*& p)
 {
-    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    if (p) pem_free_bytes(ctx, (void*)p);
     p = nullptr;
 }
 
@@ -107,16 +117,15 @@ struct pem_result {
     int32_t* tile_row = nullptr;      // [tiles]
     int32_t* tile_col = nullptr;      // [tiles]
     int64_t* pair_ptr = nullptr;      // [tiles+1]
-    int32_t* pairs_a = nullptr;       // [pairs]
-    int32_t* pairs_b = nullptr;       // [pairs]
+    int2* pair_list = nullptr;        // [pairs] (A tile id, B tile id), ascending A tile id inside a C' tile
     uint16_t* masks = nullptr;        // [tiles*16]
     int64_t* tile_nnz_ptr = nullptr;  // [tiles+1]
-    uint8_t* row_col_idx = nullptr;   // [nnz]
+    uint8_t* row_col_idx = nullptr;   // [nnz], produced on demand (pem_result_make_rowcolidx)
+    uint32_t* pair_hit = nullptr;     // [pairs] entry-owner variant: (C rows hit << 16) | C columns hit by the pair
+    int32_t* blk_tile = nullptr;      // entry-owner variant: first tile of each 256-entry step-3 block
     double* vals = nullptr;           // [nnz]
-    int32_t* blk_tile = nullptr;      // [ceil(nnz/PEM_S3_ENTRIES)+1] first tile of each step-3 block
 };
 
-enum { PEM_S3_ENTRIES = 256 };  // C entries per step-3 thread block (>= 256 so a tile spans <= 2 blocks)
 
 // scalars slots in ctx->d_scalars / h_scalars
 enum {
@@ -126,8 +135,11 @@ enum {
     SC_MAXP = 3,      // step 1: max tile products of a row
     SC_MAXD = 4,      // step 1: max C' tiles of a row
     SC_SUMP = 5,      // step 1: total tile products
-    SC_T0 = 6, SC_T1 = 7, SC_T2 = 8
+    SC_T0 = 6, SC_T1 = 7, SC_T2 = 8,
+    SC_NSMALL1 = 9, SC_NLARGE1 = 10,  // step 1: rows per kernel-2 list
+    SC_NSMALL2 = 11, SC_NLARGE2 = 12  // step 1: rows per kernel-3 list
 };
 
 // step entry points implemented in spgemm.cu / convert.cu / export.cu
 int pem_scan_exclusive_i64(pem_ctx* ctx, int64_t* d_inout, int64_t n);  // in place, n elements
+extern "C" int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C);

@@ -1,11 +1,6 @@
 // The three SpGEMM steps on tiled operands (one iteration of /root/reference/spgemm.cu:1133-1357).
 //
-//   step 1  tile-level symbolic: C' = structure(A' * B') with its ordered (A tile, B tile) pair
-//           lists.  Replaces tile_spgemm_step1_cuda_spa_kernel / ..._numeric_... (:271-384), the
-//           NSPARSE hash path (NSPARSE/spgemm_nsparse_kernel.h) AND the CSC-based pair search
-//           pem_spgemm_step2_search_pairs (:387-497): the row-wise expansion that finds a C' tile
-//           also enumerates its pairs, so the sorted-list intersection with its binary searches
-//           (and B's tile-level CSC, :1033-1062) is not needed at all.
+//   step 1  tile-level symbolic: lives in step1.cu.
 //   step 2  per-tile bitmask symbolic: C tile masks, per-tile nnz, scan, rowColIdx.  Replaces
 //           pem_spgemm_step2_compute_CMasksAndOffsets (:499-550) and ..._CrowColIdx (:552-591).
 //           Atomic-free.
@@ -20,275 +15,186 @@
 namespace {
 
 // =========================================================================================
-// small device helpers
+// Thread mapping of steps 2 and 3: SIXTEEN LANES PER C' TILE, lane = row r of the tile (two tiles
+// per warp).  The lane owns row r of the C tile, so no two threads ever update the same C entry:
+// atomic-free and, because a lane visits its tile's pairs in list order (ascending k across
+// tiles) and the set bits of Amask[r] in ascending k inside a tile, every C entry is accumulated
+// in exactly the oracle's order.
 // =========================================================================================
-template <int THREADS>
-__device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* red /* THREADS/32 + 1 words */)
-{
-    constexpr int NW = THREADS / 32;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    unsigned s = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s += red[w];
-    __syncthreads();
-    return s;
-}
 
-// In-place exclusive scan of a[0..n) in shared memory by the whole block; `in(i)` gives the input
-// for slot i (so the input may be derived from another array).  Returns the total to all threads.
-template <int THREADS, class In>
-__device__ __forceinline__ unsigned block_scan_exclusive(unsigned* a, int n, In in, unsigned* red)
-{
-    constexpr int NW = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + THREADS - 1) / THREADS;
-    const int b = min(tid * per, n), e = min(b + per, n);
-    unsigned local = 0;
-    for (int i = b; i < e; ++i) local += in(i);
-    unsigned incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) red[warp] = incl;
-    __syncthreads();
-    unsigned woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        unsigned x = red[w];
-        if (w < warp) woff += x;
-        total += x;
-    }
-    unsigned run = woff + incl - local;
-    for (int i = b; i < e; ++i) {
-        unsigned x = in(i);
-        a[i] = run;
-        run += x;
-    }
-    __syncthreads();
-    return total;
-}
-
-// =========================================================================================
-// step 1, kernel 1: per tile row of the panel: window [jmin, jmax] of reachable tile columns
-// and the number of tile-level products P (warp per tile row)
-// =========================================================================================
+// step 2, kernel 1:  Cmask[r] = OR over pairs, OR over k in Amask[r], of Bmask[k]
+// (the boolean product of the two 16x16 bit matrices, row by row), and the tile's nnz.
 __global__ void __launch_bounds__(256)
-k_row_window(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __restrict__ Acol,
-             const int32_t* __restrict__ Brp, const int32_t* __restrict__ Bcol,
-             int2* __restrict__ win, int64_t* __restrict__ scalars)
+k_step2_masks(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+              const uint16_t* __restrict__ Amasks, const uint16_t* __restrict__ Bmasks,
+              uint16_t* __restrict__ Cmasks, int64_t* __restrict__ c_tile_nnz)
 {
-    int row = rb + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    if (row >= re) return;
-    int lane = threadIdx.x & 31;
-    int jmin = INT_MAX, jmax = -1;
-    unsigned long long P = 0;
-    for (int p = Arp[row] + lane; p < Arp[row + 1]; p += 32) {
-        int k = Acol[p];
-        int bs = Brp[k], be = Brp[k + 1];
-        if (be > bs) {
-            P += (unsigned)(be - bs);
-            jmin = min(jmin, Bcol[bs]);
-            jmax = max(jmax, Bcol[be - 1]);
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = gt >> 4;
+    const unsigned r = threadIdx.x & 15u;
+    if (t >= n_tiles) return;                       // whole 16-lane groups leave together
+    const unsigned grp = 0xFFFFu << (threadIdx.x & 16u);
+    const int64_t ps = pair_ptr[t];
+    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
+    const int2* __restrict__ pl = pairs + ps;
+    unsigned acc = 0;
+    for (unsigned i = 0; i < np; ++i) {
+        const int2 ab = pl[i];
+        unsigned m = Amasks[(unsigned)ab.x * 16u + r];
+        const uint16_t* __restrict__ bm = Bmasks + (size_t)(unsigned)ab.y * 16u;
+        while (m) {
+            const unsigned k = __ffs(m) - 1;
+            m &= m - 1;
+            acc |= bm[k];
         }
     }
+    Cmasks[t * 16 + r] = (uint16_t)acc;
+    int nnz = __popc(acc);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
-        jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
-        P += __shfl_xor_sync(0xffffffffu, P, o);
-    }
-    if (lane == 0) {
-        win[row - rb] = make_int2(jmin, jmax);
-        if (jmax >= 0) {
-            long long words = ((jmax - (jmin & ~31)) >> 5) + 1;
-            atomicMax((long long*)&scalars[SC_MAXWIN], words);
-            atomicMax((long long*)&scalars[SC_MAXP], (long long)P);
-            atomicAdd((unsigned long long*)&scalars[SC_SUMP], P);
-        }
-    }
+    for (int o = 8; o > 0; o >>= 1) nnz += __shfl_xor_sync(grp, nnz, o, 16);
+    if (r == 0) c_tile_nnz[t] = nnz;
 }
 
-// =========================================================================================
-// step 1, kernel 2 (count): block per tile row, windowed bitmap accumulator in shared memory.
-//   D[row] = number of C' tiles in the row, F[row] = number of (A tile, B tile) pairs kept.
-// A pair is dropped (unless keep_empty) when colOcc(A tile) & rowOcc(B tile) == 0, i.e. when the
-// 16x16 boolean product of the two tiles is empty.
-// =========================================================================================
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_step1_count(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __restrict__ Acol,
-              const uint16_t* __restrict__ AcolOcc, const int32_t* __restrict__ Brp,
-              const int32_t* __restrict__ Bcol, const uint16_t* __restrict__ BrowOcc,
-              const int2* __restrict__ win, int keep_empty,
-              int64_t* __restrict__ D, int64_t* __restrict__ F, int64_t* __restrict__ scalars)
-{
-    extern __shared__ unsigned sm[];
-    __shared__ unsigned red[THREADS / 32 + 1];
-    constexpr int NW = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int row = rb + blockIdx.x; row < re; row += gridDim.x) {
-        int2 wnd = win[row - rb];
-        if (wnd.y < 0) {
-            if (tid == 0) { D[row - rb] = 0; F[row - rb] = 0; }
-            continue;
-        }
-        const int base = wnd.x & ~31;
-        const int W = ((wnd.y - base) >> 5) + 1;
-        for (int w = tid; w < W; w += THREADS) sm[w] = 0;
-        __syncthreads();
-        unsigned f = 0;
-        const int as = Arp[row], ae = Arp[row + 1];
-        for (int p = as + warp; p < ae; p += NW) {
-            const int k = Acol[p];
-            const unsigned aocc = keep_empty ? 0xFFFFu : AcolOcc[p];
-            const int bs = Brp[k], be = Brp[k + 1];
-            for (int q = bs + lane; q < be; q += 32) {
-                if (aocc & BrowOcc[q]) {
-                    int j = Bcol[q] - base;
-                    atomicOr(&sm[j >> 5], 1u << (j & 31));
-                    ++f;
-                }
-            }
-        }
-        __syncthreads();
-        unsigned d = 0;
-        for (int w = tid; w < W; w += THREADS) d += __popc(sm[w]);
-        d = block_sum<THREADS>(d, red);
-        f = block_sum<THREADS>(f, red);
-        if (tid == 0) {
-            D[row - rb] = d;
-            F[row - rb] = f;
-            atomicMax((long long*)&scalars[SC_MAXD], (long long)d);
-        }
-    }
-}
-
-// =========================================================================================
-// step 1, kernel 3 (fill): block per tile row.  Rebuilds the window bitmap, ranks every kept
-// product by its tile column (prefix popcount = position in the ascending C' column list),
-// counts pairs per C' tile, scans, emits C' (row, col, pair offset) and finally places the pairs
-// in ascending-k order: the A tiles of the row are visited in order and, within one A tile, all
-// B tiles have distinct columns, so `off[rank]++` needs no atomics.
-// Shared memory: bitmap[Wmax] | prefix[Wmax] | cnt[cap]   (cnt falls back to global scratch when
-// a row has more than `cap` C' tiles).
-// =========================================================================================
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_step1_fill(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __restrict__ Acol,
-             const uint16_t* __restrict__ AcolOcc, const int32_t* __restrict__ Brp,
-             const int32_t* __restrict__ Bcol, const uint16_t* __restrict__ BrowOcc,
-             const int2* __restrict__ win, int keep_empty, int Wmax, int cap,
-             unsigned* __restrict__ gcnt, size_t gcnt_stride,
-             const int64_t* __restrict__ c_row_ptr, const int64_t* __restrict__ pair_row_ptr,
-             int32_t* __restrict__ c_tile_row, int32_t* __restrict__ c_tile_col,
-             int64_t* __restrict__ pair_ptr, int32_t* __restrict__ pairs_a, int32_t* __restrict__ pairs_b)
-{
-    extern __shared__ unsigned sm[];
-    __shared__ unsigned red[THREADS / 32 + 1];
-    constexpr int NW = THREADS / 32;
-    unsigned* bitmap = sm;
-    unsigned* prefix = sm + Wmax;
-    unsigned* cnt_sm = sm + 2 * (size_t)Wmax;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int row = rb + blockIdx.x; row < re; row += gridDim.x) {
-        const int64_t cbase = c_row_ptr[row - rb];
-        const int D = (int)(c_row_ptr[row - rb + 1] - cbase);
-        if (D == 0) continue;
-        const int64_t pbase = pair_row_ptr[row - rb];
-        const int2 wnd = win[row - rb];
-        const int base = wnd.x & ~31;
-        const int W = ((wnd.y - base) >> 5) + 1;
-        unsigned* cnt = (D <= cap) ? cnt_sm : gcnt + (size_t)blockIdx.x * gcnt_stride;
-        for (int w = tid; w < W; w += THREADS) bitmap[w] = 0;
-        for (int i = tid; i < D; i += THREADS) cnt[i] = 0;
-        __syncthreads();
-        const int as = Arp[row], ae = Arp[row + 1];
-        // pass A: structure
-        for (int p = as + warp; p < ae; p += NW) {
-            const int k = Acol[p];
-            const unsigned aocc = keep_empty ? 0xFFFFu : AcolOcc[p];
-            const int bs = Brp[k], be = Brp[k + 1];
-            for (int q = bs + lane; q < be; q += 32)
-                if (aocc & BrowOcc[q]) {
-                    int j = Bcol[q] - base;
-                    atomicOr(&bitmap[j >> 5], 1u << (j & 31));
-                }
-        }
-        __syncthreads();
-        block_scan_exclusive<THREADS>(prefix, W, [&](int i) { return (unsigned)__popc(bitmap[i]); }, red);
-        // pass B: pairs per C' tile
-        for (int p = as + warp; p < ae; p += NW) {
-            const int k = Acol[p];
-            const unsigned aocc = keep_empty ? 0xFFFFu : AcolOcc[p];
-            const int bs = Brp[k], be = Brp[k + 1];
-            for (int q = bs + lane; q < be; q += 32)
-                if (aocc & BrowOcc[q]) {
-                    int j = Bcol[q] - base;
-                    int w = j >> 5;
-                    unsigned rank = prefix[w] + __popc(bitmap[w] & ((1u << (j & 31)) - 1u));
-                    atomicAdd(&cnt[rank], 1u);
-                }
-        }
-        __syncthreads();
-        block_scan_exclusive<THREADS>(cnt, D, [&](int i) { return cnt[i]; }, red);
-        // emit the C' tiles of this row (columns ascending) with their pair offsets
-        for (int w = tid; w < W; w += THREADS) {
-            unsigned m = bitmap[w];
-            unsigned r = prefix[w];
-            while (m) {
-                int b = __ffs(m) - 1;
-                m &= m - 1;
-                c_tile_row[cbase + r] = row;
-                c_tile_col[cbase + r] = base + w * 32 + b;
-                pair_ptr[cbase + r] = pbase + cnt[r];
-                ++r;
-            }
-        }
-        __syncthreads();
-        // pass C: ordered placement, A tiles in ascending k
-        for (int p = as; p < ae; ++p) {
-            const int k = Acol[p];
-            const unsigned aocc = keep_empty ? 0xFFFFu : AcolOcc[p];
-            const int bs = Brp[k], be = Brp[k + 1];
-            for (int q = bs + tid; q < be; q += THREADS)
-                if (aocc & BrowOcc[q]) {
-                    int j = Bcol[q] - base;
-                    int w = j >> 5;
-                    unsigned rank = prefix[w] + __popc(bitmap[w] & ((1u << (j & 31)) - 1u));
-                    unsigned pos = cnt[rank]++;
-                    pairs_a[pbase + pos] = p;
-                    pairs_b[pbase + pos] = q;
-                }
-            __syncthreads();
-        }
-    }
-}
-
-// =========================================================================================
-// step 2, kernel 1: one thread per C' tile: mask of the tile = OR over its pairs of the boolean
-// product of the two 16x16 bit matrices, computed as  Cmask[r] |= OR_{k in Amask[r]} Bmask[k].
-// =========================================================================================
+// Ctiles_rowColIdx ((r<<4)|c per nonzero, row-major inside a tile): part of the reference's data
+// contract (spgemm.cu:552-591) but read by nothing in this engine, so it is produced on demand
+// only (pem_result_get / tests).  One thread per C' tile, bytes assembled eight at a time.
 __global__ void __launch_bounds__(128)
-k_step2_masks(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int32_t* __restrict__ pairs_a,
-              const int32_t* __restrict__ pairs_b, const uint16_t* __restrict__ Amasks,
-              const uint16_t* __restrict__ Bmasks, uint16_t* __restrict__ Cmasks,
-              int64_t* __restrict__ c_tile_nnz)
+k_rowcolidx(int64_t n_tiles, const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
+            uint8_t* __restrict__ row_col_idx)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint4* m4 = reinterpret_cast<const uint4*>(Cmasks + (size_t)t * 16);
+    const uint4 x = m4[0], y = m4[1];
+    const unsigned w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    uint8_t* dst = row_col_idx + c_tile_nnz_ptr[t];
+    int head = (int)((8 - ((uintptr_t)dst & 7)) & 7);   // single bytes until dst is 8-byte aligned
+    unsigned long long buf = 0;
+    int nb = 0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        unsigned m = (w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
+        while (m) {
+            const unsigned c = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned byte = (r << 4) | c;
+            if (head > 0) {
+                *dst++ = (uint8_t)byte;
+                --head;
+            } else {
+                buf |= (unsigned long long)byte << (8 * nb);
+                if (++nb == 8) {
+                    *reinterpret_cast<unsigned long long*>(dst) = buf;
+                    dst += 8;
+                    buf = 0;
+                    nb = 0;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < nb; ++i) dst[i] = (uint8_t)(buf >> (8 * i));
+}
+
+// step 3: numeric.  Lane r keeps the 16 accumulators of its C row in shared memory, column-major
+// over threads (acc[c][tid]) so that a warp's accesses never conflict beyond the 2 wavefronts a
+// 64-bit access needs; only the columns present in Cmask[r] are ever touched.  For every pair, every
+// k in Amask[r] (ascending; the A values of the row are consecutive), every c in Bmask[k]
+// (ascending; the B values of the row are consecutive):  acc[c] = fma(a, b, acc[c]).
+// Replaces pem_spgemm_step3_accumulate (spgemm.cu:593-661): no global read-modify-write per
+// product, no per-product popcount index arithmetic, C written once, sequentially per row.
+constexpr int S3_THREADS = 256;
+
+__global__ void __launch_bounds__(S3_THREADS)
+k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+                const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
+                const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
+                const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
+                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
+                const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
+                double* __restrict__ C_vals)
+{
+    __shared__ double acc[16][S3_THREADS];
+    const int tid = threadIdx.x;
+    const int64_t t = ((int64_t)blockIdx.x * S3_THREADS + tid) >> 4;
+    const unsigned r = tid & 15u;
+    if (t >= n_tiles) return;                       // whole 16-lane groups leave together
+    const unsigned grp = 0xFFFFu << (tid & 16);
+    const unsigned cm = Cmasks[t * 16 + r];
+    // offset of row r inside the tile: exclusive scan of the row popcounts over the 16 lanes
+    const int pc = __popc(cm);
+    int incl = pc;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(grp, incl, o, 16);
+        if ((int)r >= o) incl += v;
+    }
+    if (cm == 0) return;                            // nothing lands in this row
+    for (unsigned m = cm; m;) {
+        const unsigned c = __ffs(m) - 1;
+        m &= m - 1;
+        acc[c][tid] = 0.0;
+    }
+    const int64_t ps = pair_ptr[t];
+    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
+    const int2* __restrict__ pl = pairs + ps;
+    for (unsigned i = 0; i < np; ++i) {
+        const int2 ab = pl[i];
+        const unsigned ia = (unsigned)ab.x * 16u;
+        unsigned am = A_masks[ia + r];
+        if (am) {
+            const unsigned ib = (unsigned)ab.y * 16u;
+            const double* __restrict__ ap = A_vals + (A_off[ab.x] + A_rowptr[ia + r]);
+            const double* __restrict__ bbase = B_vals + B_off[ab.y];
+            do {
+                const unsigned k = __ffs(am) - 1;
+                am &= am - 1;
+                const double a = *ap++;
+                unsigned bm = B_masks[ib + k];
+                const double* __restrict__ bp = bbase + B_rowptr[ib + k];
+                while (bm) {
+                    const unsigned c = __ffs(bm) - 1;
+                    bm &= bm - 1;
+                    acc[c][tid] = fma(a, *bp++, acc[c][tid]);
+                }
+            } while (am);
+        }
+    }
+    double* __restrict__ out = C_vals + c_tile_nnz_ptr[t] + (incl - pc);
+    for (unsigned m = cm; m;) {
+        const unsigned c = __ffs(m) - 1;
+        m &= m - 1;
+        *out++ = acc[c][tid];
+    }
+}
+
+// =========================================================================================
+// Entry-owner variant of steps 2 and 3 (default): one thread per C' tile for the masks, one
+// thread per C NONZERO for the values.  Dense lane packing: every lane of every warp owns real
+// work, which is what wins on hypersparse tiles (1-3 nonzeros per tile).
+// =========================================================================================
+
+// step 2, kernel 1 (tile-owner): as k_step2_masks, plus per pair which rows and columns of the C
+// tile the pair contributes to (pair_hit = rows << 16 | cols): the entry-owner step 3 uses it to
+// skip pairs that cannot touch a given entry.
+__global__ void __launch_bounds__(128)
+k_step2_masks_tile(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+                   const uint16_t* __restrict__ Amasks, const uint16_t* __restrict__ Bmasks,
+                   uint16_t* __restrict__ Cmasks, int64_t* __restrict__ c_tile_nnz, uint32_t* __restrict__ pair_hit)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
-    for (int64_t pp = ps; pp < pe; ++pp) {
-        const int a = pairs_a[pp], b = pairs_b[pp];
-        const uint4* am4 = reinterpret_cast<const uint4*>(Amasks + (size_t)a * 16);
+    const int64_t ps = pair_ptr[t];
+    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
+    const int2* __restrict__ pl = pairs + ps;
+    uint32_t* __restrict__ hl = pair_hit + ps;
+    for (unsigned i = 0; i < np; ++i) {
+        const int2 ab = pl[i];
+        const uint4* am4 = reinterpret_cast<const uint4*>(Amasks + (size_t)(unsigned)ab.x * 16u);
         const uint4 x = am4[0], y = am4[1];
         const unsigned aw[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-        const uint16_t* __restrict__ bm = Bmasks + (size_t)b * 16;
+        const uint16_t* __restrict__ bm = Bmasks + (size_t)(unsigned)ab.y * 16u;
+        unsigned rows_hit = 0, cols_hit = 0;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             unsigned m = (aw[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
@@ -299,7 +205,10 @@ k_step2_masks(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int32
                 o |= bm[k];
             }
             acc[r >> 1] |= o << ((r & 1) * 16);
+            cols_hit |= o;
+            rows_hit |= (o ? 1u : 0u) << r;
         }
+        hl[i] = (rows_hit << 16) | cols_hit;
     }
     uint4* out = reinterpret_cast<uint4*>(Cmasks + (size_t)t * 16);
     out[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
@@ -310,82 +219,94 @@ k_step2_masks(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int32
     c_tile_nnz[t] = nnz;
 }
 
-// =========================================================================================
-// step 2, kernel 2: one thread per C' tile: Ctiles_rowColIdx ((r<<4)|c per nonzero, row-major)
-// and the first tile of every step-3 block (a tile holds <= 256 = PEM_S3_ENTRIES nonzeros, so it
-// covers at most one block boundary).
-// =========================================================================================
-__global__ void __launch_bounds__(128)
-k_step2_rowcolidx(int64_t n_tiles, const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
-                  uint8_t* __restrict__ row_col_idx, int32_t* __restrict__ blk_tile)
+// first tile of every entry-owner step-3 block (a tile holds <= 256 = S3E_ENTRIES nonzeros, so it
+// covers at most one block boundary)
+constexpr int S3E_ENTRIES = 256;
+__global__ void __launch_bounds__(256)
+k_block_tiles(int64_t n_tiles, const int64_t* __restrict__ c_tile_nnz_ptr, int32_t* __restrict__ blk_tile)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const uint4* m4 = reinterpret_cast<const uint4*>(Cmasks + (size_t)t * 16);
-    const uint4 x = m4[0], y = m4[1];
-    const unsigned w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    int64_t off = c_tile_nnz_ptr[t];
-    const int64_t end = c_tile_nnz_ptr[t + 1];
+    const int64_t off = c_tile_nnz_ptr[t], end = c_tile_nnz_ptr[t + 1];
     if (end > off) {
-        int64_t bnd = (off + PEM_S3_ENTRIES - 1) / PEM_S3_ENTRIES * PEM_S3_ENTRIES;
-        if (bnd < end) blk_tile[bnd / PEM_S3_ENTRIES] = (int32_t)t;
-    }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        unsigned m = (w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
-        while (m) {
-            int c = __ffs(m) - 1;
-            m &= m - 1;
-            row_col_idx[off++] = (uint8_t)((r << 4) | c);
-        }
+        int64_t bnd = (off + S3E_ENTRIES - 1) / S3E_ENTRIES * S3E_ENTRIES;
+        if (bnd < end) blk_tile[bnd / S3E_ENTRIES] = (int32_t)t;
     }
 }
 
-// =========================================================================================
-// step 3: one thread per C nonzero.  The block covers PEM_S3_ENTRIES consecutive nonzeros; a
-// thread finds its tile by binary search in the tile offset array between the block's first tile
-// and the next block's first tile, then walks the tile's pair list in order:
+// step 3 (entry-owner): the block covers S3E_ENTRIES consecutive nonzeros; the offsets of the
+// tiles it overlaps are staged in shared memory and each thread finds its tile by binary search
+// there.  A thread then walks its tile's pair list in order, skipping pairs whose hit word rules its
+// (r, c) out, and for each remaining pair
 //   m = Amask[r] & BmaskT[c];  for each k in m (ascending):  acc = fma(a_rk, b_kc, acc)
 // Same product order as the reference (:648-656) and as the host oracle; C is written once.
-// =========================================================================================
-__global__ void __launch_bounds__(PEM_S3_ENTRIES)
-k_step3_numeric(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
+constexpr int S3E_TMAX = 512;
+
+__global__ void __launch_bounds__(S3E_ENTRIES)
+k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
                 const int64_t* __restrict__ c_tile_nnz_ptr, const uint8_t* __restrict__ row_col_idx,
-                const int64_t* __restrict__ pair_ptr, const int32_t* __restrict__ pairs_a,
-                const int32_t* __restrict__ pairs_b,
+                const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+                const uint32_t* __restrict__ pair_hit,
                 const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
                 const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
                 const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
                 const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
                 const uint16_t* __restrict__ B_masks_t, double* __restrict__ C_vals)
 {
-    const int64_t n = (int64_t)blockIdx.x * PEM_S3_ENTRIES + threadIdx.x;
+    __shared__ int s_off[S3E_TMAX];
+    const int tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * S3E_ENTRIES;
+    const int64_t t0 = blk_tile[blockIdx.x];
+    const int64_t t1 = (n0 + S3E_ENTRIES < nnz) ? (int64_t)blk_tile[blockIdx.x + 1] : n_tiles - 1;
+    const int64_t span = t1 - t0 + 1;
+    const bool staged = span <= S3E_TMAX;
+    if (staged)
+        for (int i = tid; i < (int)span; i += S3E_ENTRIES) s_off[i] = (int)(c_tile_nnz_ptr[t0 + i] - n0);
+    __syncthreads();
+    const int64_t n = n0 + tid;
     if (n >= nnz) return;
-    // last tile t in [lo, hi] with c_tile_nnz_ptr[t] <= n
-    int64_t lo = blk_tile[blockIdx.x];
-    int64_t hi = ((int64_t)(blockIdx.x + 1) * PEM_S3_ENTRIES < nnz) ? blk_tile[blockIdx.x + 1] : n_tiles - 1;
-    while (lo < hi) {
-        int64_t mid = (lo + hi + 1) >> 1;
-        if (c_tile_nnz_ptr[mid] <= n) lo = mid; else hi = mid - 1;
+    int64_t t;
+    if (staged) {                                   // last i with s_off[i] <= tid
+        int lo = 0, hi = (int)span - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= tid) lo = mid; else hi = mid - 1;
+        }
+        t = t0 + lo;
+    } else {                                        // many empty tiles in range (keep_empty mode)
+        int64_t lo = t0, hi = t1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (c_tile_nnz_ptr[mid] <= n) lo = mid; else hi = mid - 1;
+        }
+        t = lo;
     }
-    const int64_t t = lo;
     const unsigned rc = row_col_idx[n];
     const unsigned r = rc >> 4, c = rc & 15u;
     const unsigned below_c = (1u << c) - 1u;
+    const unsigned want = (0x10000u << r) | (1u << c);
+    const int64_t ps = pair_ptr[t];
+    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
+    const int2* __restrict__ pl = pairs + ps;
+    const uint32_t* __restrict__ hl = pair_hit + ps;
     double acc = 0.0;
-    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
-    for (int64_t pp = ps; pp < pe; ++pp) {
-        const int a = pairs_a[pp], b = pairs_b[pp];
-        const unsigned am = A_masks[(size_t)a * 16 + r];
-        unsigned m = am & B_masks_t[(size_t)b * 16 + c];
+    unsigned i = 0;
+    for (;;) {
+        while (i < np && (hl[i] & want) != want) ++i;       // cheap skip loop
+        if (i >= np) break;
+        const int2 ab = pl[i];
+        ++i;
+        const unsigned ia = (unsigned)ab.x * 16u, ib = (unsigned)ab.y * 16u;
+        const unsigned am = A_masks[ia + r];
+        unsigned m = am & B_masks_t[ib + c];
         if (m) {
-            const double* __restrict__ av = A_vals + A_off[a] + A_rowptr[(size_t)a * 16 + r];
-            const double* __restrict__ bv = B_vals + B_off[b];
+            const double* __restrict__ av = A_vals + (A_off[ab.x] + A_rowptr[ia + r]);
+            const double* __restrict__ bv = B_vals + B_off[ab.y];
             do {
-                const int k = __ffs(m) - 1;
+                const unsigned k = __ffs(m) - 1;
                 m &= m - 1;
-                const int ao = __popc(am & ((1u << k) - 1u));
-                const int bo = B_rowptr[(size_t)b * 16 + k] + __popc(B_masks[(size_t)b * 16 + k] & below_c);
+                const unsigned ao = __popc(am & ((1u << k) - 1u));
+                const unsigned bo = B_rowptr[ib + k] + __popc(B_masks[ib + k] & below_c);
                 acc = fma(av[ao], bv[bo], acc);
             } while (m);
         }
@@ -410,106 +331,6 @@ static int check_operands(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, 
 
 extern "C" {
 
-int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
-                       int32_t rb, int32_t re, pem_result** out)
-{
-    if (!out) return PEM_ERR_ARG;
-    *out = nullptr;
-    PEM_TRY(check_operands(ctx, A, B, rb, re));
-    PEM_CK(cudaSetDevice(ctx->device));
-    pem_result* C = new pem_result();
-    C->rb = rb; C->re = re; C->rows = A->rows; C->cols = B->cols; C->tile_cols = B->tile_cols;
-    auto fail = [&](int rc) { pem_result_free(ctx, C); return rc; };
-#define S_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) return fail(rc_); } while (0)
-#define S_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx->fail_cuda(e_, #call, __FILE__, __LINE__)); } while (0)
-    const int nrows = re - rb;
-    S_TRY(pem_alloc(ctx, &C->row_ptr, (size_t)nrows + 1));
-    int64_t* pair_row_ptr = nullptr;
-    int2* win = nullptr;
-    S_TRY(pem_alloc(ctx, &pair_row_ptr, (size_t)nrows + 1));
-    S_TRY(pem_alloc(ctx, &win, (size_t)nrows));
-    S_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
-    S_CK(cudaMemsetAsync(C->row_ptr, 0, ((size_t)nrows + 1) * 8, ctx->stream));
-    S_CK(cudaMemsetAsync(pair_row_ptr, 0, ((size_t)nrows + 1) * 8, ctx->stream));
-    auto cleanup_tmp = [&]() { pem_free(ctx, pair_row_ptr); pem_free(ctx, win); };
-
-    int64_t maxwin = 0, maxd = 0;
-    if (nrows > 0 && A->tiles > 0 && B->tiles > 0) {
-        k_row_window<<<pem_div_up((int64_t)nrows * 32, 256), 256, 0, ctx->stream>>>(
-            rb, re, A->tile_row_ptr, A->tile_col_idx, B->tile_row_ptr, B->tile_col_idx, win, ctx->d_scalars);
-        ++ctx->launches;
-        S_CK(cudaGetLastError());
-        S_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        S_CK(cudaStreamSynchronize(ctx->stream));
-        maxwin = ctx->h_scalars[SC_MAXWIN];
-        C->tile_products = ctx->h_scalars[SC_SUMP];
-    }
-    constexpr int TH = 128;
-    if (maxwin > 0) {
-        size_t smem_count = (size_t)maxwin * 4;
-        if (smem_count > (size_t)ctx->smem_optin) {
-            cleanup_tmp();
-            return fail(ctx->fail(PEM_ERR_LIMIT, "step 1: column window of a tile row exceeds the shared-memory bitmap"));
-        }
-        S_CK(cudaFuncSetAttribute(k_step1_count<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
-        int grid = (int)std::min<int64_t>(nrows, (int64_t)ctx->sm_count * 64);
-        k_step1_count<TH><<<grid, TH, smem_count, ctx->stream>>>(
-            rb, re, A->tile_row_ptr, A->tile_col_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx, B->row_occ,
-            win, ctx->opt_keep_empty, C->row_ptr, pair_row_ptr, ctx->d_scalars);
-        ++ctx->launches;
-        S_CK(cudaGetLastError());
-        S_TRY(pem_scan_exclusive_i64(ctx, C->row_ptr, (int64_t)nrows + 1));
-        S_TRY(pem_scan_exclusive_i64(ctx, pair_row_ptr, (int64_t)nrows + 1));
-        S_CK(cudaMemcpyAsync(&ctx->d_scalars[SC_T0], C->row_ptr + nrows, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        S_CK(cudaMemcpyAsync(&ctx->d_scalars[SC_T1], pair_row_ptr + nrows, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        S_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        S_CK(cudaStreamSynchronize(ctx->stream));
-        C->tiles = ctx->h_scalars[SC_T0];
-        C->pairs = ctx->h_scalars[SC_T1];
-        maxd = ctx->h_scalars[SC_MAXD];
-    }
-    S_TRY(pem_alloc(ctx, &C->tile_row, (size_t)C->tiles));
-    S_TRY(pem_alloc(ctx, &C->tile_col, (size_t)C->tiles));
-    S_TRY(pem_alloc(ctx, &C->pair_ptr, (size_t)C->tiles + 1));
-    S_TRY(pem_alloc(ctx, &C->pairs_a, (size_t)C->pairs));
-    S_TRY(pem_alloc(ctx, &C->pairs_b, (size_t)C->pairs));
-    if (C->tiles > 0) {
-        const int cap_default = 4096;
-        size_t smem_fill = (size_t)maxwin * 8 + (size_t)cap_default * 4;
-        int cap = cap_default;
-        if (smem_fill > (size_t)ctx->smem_optin) {
-            cap = 0;
-            smem_fill = (size_t)maxwin * 8;
-            if (smem_fill > (size_t)ctx->smem_optin) {
-                cleanup_tmp();
-                return fail(ctx->fail(PEM_ERR_LIMIT, "step 1: column window of a tile row exceeds the shared-memory bitmap"));
-            }
-        }
-        int grid = (int)std::min<int64_t>(nrows, (int64_t)ctx->sm_count * 8);
-        unsigned* gcnt = nullptr;
-        size_t stride = 0;
-        if (maxd > cap) {
-            stride = (size_t)maxd;
-            S_TRY(pem_alloc(ctx, &gcnt, stride * (size_t)grid));
-        }
-        S_CK(cudaFuncSetAttribute(k_step1_fill<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fill));
-        k_step1_fill<TH><<<grid, TH, smem_fill, ctx->stream>>>(
-            rb, re, A->tile_row_ptr, A->tile_col_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx, B->row_occ,
-            win, ctx->opt_keep_empty, (int)maxwin, cap, gcnt, stride, C->row_ptr, pair_row_ptr,
-            C->tile_row, C->tile_col, C->pair_ptr, C->pairs_a, C->pairs_b);
-        ++ctx->launches;
-        S_CK(cudaGetLastError());
-        pem_free(ctx, gcnt);
-    }
-    k_set_last_i64<<<1, 1, 0, ctx->stream>>>(C->pair_ptr, C->tiles, C->pairs);
-    ++ctx->launches;
-    S_CK(cudaGetLastError());
-    cleanup_tmp();
-    C->stage = 1;
-    *out = C;
-    return PEM_OK;
-}
-
 int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
 {
     if (!ctx || !A || !B || !C) return PEM_ERR_ARG;
@@ -517,9 +338,15 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_alloc(ctx, &C->masks, (size_t)C->tiles * 16));
     PEM_TRY(pem_alloc(ctx, &C->tile_nnz_ptr, (size_t)C->tiles + 1));
-    if (C->tiles > 0) {
-        k_step2_masks<<<pem_div_up(C->tiles, 128), 128, 0, ctx->stream>>>(
-            C->tiles, C->pair_ptr, C->pairs_a, C->pairs_b, A->masks, B->masks, C->masks, C->tile_nnz_ptr);
+    const bool rows_variant = ctx->opt_owner == 1;
+    if (!rows_variant) PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)C->pairs));
+    if (C->tiles > 0 && rows_variant) {
+        k_step2_masks<<<pem_div_up(C->tiles * 16, 256), 256, 0, ctx->stream>>>(
+            C->tiles, C->pair_ptr, C->pair_list, A->masks, B->masks, C->masks, C->tile_nnz_ptr);
+        PEM_LAUNCHED();
+    } else if (C->tiles > 0) {
+        k_step2_masks_tile<<<pem_div_up(C->tiles, 128), 128, 0, ctx->stream>>>(
+            C->tiles, C->pair_ptr, C->pair_list, A->masks, B->masks, C->masks, C->tile_nnz_ptr, C->pair_hit);
         PEM_LAUNCHED();
     }
     k_set_last_i64<<<1, 1, 0, ctx->stream>>>(C->tile_nnz_ptr, C->tiles, 0);
@@ -528,15 +355,16 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     PEM_CK(cudaMemcpyAsync(ctx->h_scalars, C->tile_nnz_ptr + C->tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     C->nnz = ctx->h_scalars[0];
-    PEM_TRY(pem_alloc(ctx, &C->row_col_idx, (size_t)C->nnz));
-    int64_t nblk = (C->nnz + PEM_S3_ENTRIES - 1) / PEM_S3_ENTRIES;
-    PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
-    if (C->tiles > 0) {
-        k_step2_rowcolidx<<<pem_div_up(C->tiles, 128), 128, 0, ctx->stream>>>(
-            C->tiles, C->masks, C->tile_nnz_ptr, C->row_col_idx, C->blk_tile);
-        PEM_LAUNCHED();
-    }
     C->stage = 2;
+    if (!rows_variant) {          // what the entry-owner step 3 reads: (r,c) per nonzero, first tile per block
+        PEM_TRY(pem_result_make_rowcolidx(ctx, C));
+        const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
+        PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
+        if (C->tiles > 0) {
+            k_block_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->tile_nnz_ptr, C->blk_tile);
+            PEM_LAUNCHED();
+        }
+    }
     return PEM_OK;
 }
 
@@ -546,16 +374,38 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
     if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
-    if (C->nnz > 0) {
-        int64_t nblk = (C->nnz + PEM_S3_ENTRIES - 1) / PEM_S3_ENTRIES;
+    if (C->nnz > 0 && C->pair_hit) {      // entry-owner variant (step 2 prepared its inputs)
+        const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^39 nonzeros");
-        k_step3_numeric<<<(unsigned)nblk, PEM_S3_ENTRIES, 0, ctx->stream>>>(
-            C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, C->row_col_idx, C->pair_ptr, C->pairs_a, C->pairs_b,
+        k_step3_entries<<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(
+            C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, C->row_col_idx, C->pair_ptr, C->pair_list, C->pair_hit,
             A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr,
             B->masks_t, C->vals);
         PEM_LAUNCHED();
+    } else if (C->tiles > 0) {
+        const int64_t nblk = (C->tiles * 16 + S3_THREADS - 1) / S3_THREADS;
+        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^35 tiles");
+        k_step3_numeric<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(
+            C->tiles, C->pair_ptr, C->pair_list, C->masks, C->tile_nnz_ptr,
+            A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr, C->vals);
+        PEM_LAUNCHED();
     }
     C->stage = 3;
+    return PEM_OK;
+}
+
+// Ctiles_rowColIdx on demand (see k_rowcolidx)
+int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C)
+{
+    if (!ctx || !C) return PEM_ERR_ARG;
+    if (C->stage < 2) return ctx->fail(PEM_ERR_ARG, "rowColIdx needs step 2");
+    if (C->row_col_idx) return PEM_OK;
+    PEM_CK(cudaSetDevice(ctx->device));
+    PEM_TRY(pem_alloc(ctx, &C->row_col_idx, (size_t)C->nnz));
+    if (C->tiles > 0) {
+        k_rowcolidx<<<pem_div_up(C->tiles, 128), 128, 0, ctx->stream>>>(C->tiles, C->masks, C->tile_nnz_ptr, C->row_col_idx);
+        PEM_LAUNCHED();
+    }
     return PEM_OK;
 }
 

@@ -195,3 +195,24 @@ def test_device_pointer_input_and_pool_reuse(engine):
         _assert_same_C(C, oC)
         C.free()
     A.free()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_row_owner_variant_is_bit_identical(engine, k):
+    """PEM_OPT_OWNER=1 (sixteen lanes per C' tile) must give the same bits as the default."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+    C0 = engine.spgemm(A, B)
+    engine.set_option(pem.OPT_OWNER, 1)
+    try:
+        C1 = engine.spgemm(A, B)
+    finally:
+        engine.set_option(pem.OPT_OWNER, 0)
+    assert np.array_equal(C0.array("masks"), C1.array("masks"))
+    assert np.array_equal(C0.array("tile_nnz_ptr"), C1.array("tile_nnz_ptr"))
+    assert np.array_equal(C0.array("vals"), C1.array("vals"))
+    assert np.array_equal(C0.array("row_col_idx"), C1.array("row_col_idx"))
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    _assert_same_C(C1, oC)
+    C0.free(); C1.free(); A.free(); B.free()

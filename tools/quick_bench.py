@@ -1,0 +1,57 @@
+"""Developer timing loop: per-step times of the engine on the named configs (not the bench contract).
+    python tools/quick_bench.py 2 3 4 [--check] [--keep-empty] [--reps N]"""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pem_spgemm_b200 as pem
+from pem_spgemm_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("configs", nargs="+", type=int)
+ap.add_argument("--check", action="store_true")
+ap.add_argument("--keep-empty", type=int, default=0)
+ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--small", action="store_true")
+ap.add_argument("--owner", type=int, default=0)
+a = ap.parse_args()
+ctx = pem.Context(0)
+ctx.set_option(pem.OPT_KEEP_EMPTY_TILES, a.keep_empty)
+ctx.set_option(pem.OPT_OWNER, a.owner)
+for k in a.configs:
+    t0 = time.time()
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=a.small)
+    tg = time.time() - t0
+    tc = pem.Times()
+    A = ctx.convert_coo(rows, cols, I, J, V, times=tc)
+    B = ctx.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
+    flop = ctx.count_flop(A, B)
+    best = None
+    for r in range(a.reps):
+        t = pem.Times()
+        C = ctx.spgemm(A, B, times=t)
+        info = C.info
+        if best is None or t.total_ms < best.total_ms:
+            best = t
+        if os.environ.get('PEM_QB_VERBOSE'):
+            print(f'   rep {r}: step1 {t.step1_ms:.3f} step2 {t.step2_ms:.3f} step3 {t.step3_ms:.3f} total {t.total_ms:.3f} pool {ctx.pool_bytes/2**30:.2f} GiB', flush=True)
+        if r + 1 < a.reps:
+            C.free()
+    print(f"{name}: gen {tg:.1f}s nnzA {A.info.nnz} tilesA {A.info.tiles} flop {flop} | convert {tc.convert_total_ms:.2f} ms "
+          f"(tile kernel {tc.convert_kernel_ms:.3f}) | C tiles {info.tiles} pairs {info.pairs} nnz {info.nnz} tile_products {info.tile_products} | "
+          f"step1 {best.step1_ms:.3f} step2 {best.step2_ms:.3f} step3 {best.step3_ms:.3f} total {best.total_ms:.3f} ms "
+          f"=> {2*flop/best.total_ms/1e6:.1f} GFLOP/s | pool {ctx.pool_bytes/2**30:.2f} GiB", flush=True)
+    if a.check:
+        from oracle import host
+        oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+        s, ab = C.checksum()
+        ok = (oC.nnz == info.nnz) and host.flop(oA, oB) == flop
+        r, c, v = C.to_coo()
+        ro, co, vo = oC.to_coo()
+        ok = ok and np.array_equal(r, ro) and np.array_equal(c, co)
+        exact = ok and np.array_equal(v, vo)
+        print(f"   check vs oracle: structure {'OK' if ok else 'MISMATCH'}, values {'bit-exact' if exact else 'DIFFER'}", flush=True)
+    C.free()
+    if B is not A:
+        B.free()
+    A.free()
+ctx.close()

@@ -13,7 +13,7 @@
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
-enum { PEM_NSCALARS = 16, PEM_NEVENTS = 8 };
+enum { PEM_NSCALARS = 24, PEM_NEVENTS = 8 };
 
 struct pem_ctx {
     int device = 0;
@@ -137,7 +137,8 @@ enum {
     SC_SUMP = 5,      // step 1: total tile products
     SC_T0 = 6, SC_T1 = 7, SC_T2 = 8,
     SC_NSMALL1 = 9, SC_NLARGE1 = 10,  // step 1: rows per kernel-2 list
-    SC_NSMALL2 = 11, SC_NLARGE2 = 12  // step 1: rows per kernel-3 list
+    SC_NSMALL2 = 11, SC_NLARGE2 = 12, // step 1: rows per kernel-3 list
+    SC_WORK0 = 16                     // step 1: four work-queue cursors (count large/small, fill large/small)
 };
 
 // step entry points implemented in spgemm.cu / convert.cu / export.cu

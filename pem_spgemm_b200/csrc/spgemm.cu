@@ -95,14 +95,17 @@ k_rowcolidx(int64_t n_tiles, const uint16_t* __restrict__ Cmasks, const int64_t*
     for (int i = 0; i < nb; ++i) dst[i] = (uint8_t)(buf >> (8 * i));
 }
 
-// step 3: numeric.  Lane r keeps the 16 accumulators of its C row in shared memory, column-major
-// over threads (acc[c][tid]) so that a warp's accesses never conflict beyond the 2 wavefronts a
-// 64-bit access needs; only the columns present in Cmask[r] are ever touched.  For every pair, every
-// k in Amask[r] (ascending; the A values of the row are consecutive), every c in Bmask[k]
-// (ascending; the B values of the row are consecutive):  acc[c] = fma(a, b, acc[c]).
+// step 3 (row-owner): numeric.  Lane r accumulates its C row in FOUR REGISTERS: the nonzeros of
+// the row are numbered by rank inside Cmask[r] and handled four ranks per pass (nearly every row of
+// a sparse product has <= 4 nonzeros per tile, i.e. one pass; a fully dense row takes four).  No
+// shared memory, so the kernel keeps full occupancy and the whole L1.  For every pair (the next
+// pair's ids and A row mask are prefetched), every k in Amask[r] (ascending; the A values of the row
+// are consecutive), every c in Bmask[k] that belongs to the pass (ascending):
+//     acc[rank(c)] = fma(a, b, acc[rank(c)])
 // Replaces pem_spgemm_step3_accumulate (spgemm.cu:593-661): no global read-modify-write per
-// product, no per-product popcount index arithmetic, C written once, sequentially per row.
+// product, C written once, sequentially per row.
 constexpr int S3_THREADS = 256;
+constexpr int S3_NACC = 4;
 
 __global__ void __launch_bounds__(S3_THREADS)
 k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
@@ -113,7 +116,6 @@ k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int
                 const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
                 double* __restrict__ C_vals)
 {
-    __shared__ double acc[16][S3_THREADS];
     const int tid = threadIdx.x;
     const int64_t t = ((int64_t)blockIdx.x * S3_THREADS + tid) >> 4;
     const unsigned r = tid & 15u;
@@ -129,41 +131,64 @@ k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int
         if ((int)r >= o) incl += v;
     }
     if (cm == 0) return;                            // nothing lands in this row
-    for (unsigned m = cm; m;) {
-        const unsigned c = __ffs(m) - 1;
-        m &= m - 1;
-        acc[c][tid] = 0.0;
-    }
     const int64_t ps = pair_ptr[t];
     const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
     const int2* __restrict__ pl = pairs + ps;
-    for (unsigned i = 0; i < np; ++i) {
-        const int2 ab = pl[i];
-        const unsigned ia = (unsigned)ab.x * 16u;
-        unsigned am = A_masks[ia + r];
-        if (am) {
-            const unsigned ib = (unsigned)ab.y * 16u;
-            const double* __restrict__ ap = A_vals + (A_off[ab.x] + A_rowptr[ia + r]);
-            const double* __restrict__ bbase = B_vals + B_off[ab.y];
-            do {
-                const unsigned k = __ffs(am) - 1;
-                am &= am - 1;
-                const double a = *ap++;
-                unsigned bm = B_masks[ib + k];
-                const double* __restrict__ bp = bbase + B_rowptr[ib + k];
-                while (bm) {
-                    const unsigned c = __ffs(bm) - 1;
-                    bm &= bm - 1;
-                    acc[c][tid] = fma(a, *bp++, acc[c][tid]);
-                }
-            } while (am);
-        }
-    }
     double* __restrict__ out = C_vals + c_tile_nnz_ptr[t] + (incl - pc);
-    for (unsigned m = cm; m;) {
-        const unsigned c = __ffs(m) - 1;
-        m &= m - 1;
-        *out++ = acc[c][tid];
+    unsigned rest = cm;                             // columns not yet produced
+    for (int lo = 0; lo < pc; lo += S3_NACC) {
+        // the (up to) four lowest remaining columns form this pass
+        unsigned pm = 0;
+#pragma unroll
+        for (int j = 0; j < S3_NACC; ++j) {
+            const unsigned low = rest & (0u - rest);
+            pm |= low;
+            rest ^= low;
+        }
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        int2 ab_n = pl[0];
+        unsigned am_n = A_masks[(unsigned)ab_n.x * 16u + r];
+        for (unsigned i = 0; i < np; ++i) {
+            const int2 ab = ab_n;
+            unsigned am = am_n;
+            if (i + 1 < np) {                       // prefetch the next pair
+                ab_n = pl[i + 1];
+                am_n = A_masks[(unsigned)ab_n.x * 16u + r];
+            }
+            if (am) {
+                const unsigned ib = (unsigned)ab.y * 16u;
+                const double* __restrict__ ap = A_vals + (A_off[ab.x] + A_rowptr[(unsigned)ab.x * 16u + r]);
+                const double* __restrict__ bbase = B_vals + B_off[ab.y];
+                do {
+                    const unsigned k = __ffs(am) - 1;
+                    am &= am - 1;
+                    const unsigned bm = B_masks[ib + k];
+                    unsigned hit = bm & pm;
+                    if (hit) {
+                        const double a = *ap;
+                        const double* __restrict__ bp = bbase + B_rowptr[ib + k];
+                        do {
+                            const unsigned low = hit & (0u - hit);
+                            hit ^= low;
+                            const double b = bp[__popc(bm & (low - 1u))];
+                            const int idx = __popc(pm & (low - 1u));
+                            const double v0 = fma(a, b, acc0), v1 = fma(a, b, acc1), v2 = fma(a, b, acc2), v3 = fma(a, b, acc3);
+                            acc0 = idx == 0 ? v0 : acc0;
+                            acc1 = idx == 1 ? v1 : acc1;
+                            acc2 = idx == 2 ? v2 : acc2;
+                            acc3 = idx == 3 ? v3 : acc3;
+                        } while (hit);
+                    }
+                    ++ap;
+                } while (am);
+            }
+        }
+        const int cnt = min(S3_NACC, pc - lo);
+        out[0] = acc0;
+        if (cnt > 1) out[1] = acc1;
+        if (cnt > 2) out[2] = acc2;
+        if (cnt > 3) out[3] = acc3;
+        out += S3_NACC;
     }
 }
 

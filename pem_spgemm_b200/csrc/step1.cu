@@ -31,6 +31,8 @@
 // A pair is dropped (unless PEM_OPT_KEEP_EMPTY_TILES) when colOcc(A tile) & rowOcc(B tile) == 0:
 // the 16x16 boolean product of the two tiles is then empty, so C' holds exactly the non-empty
 // tiles of C and steps 2/3 never touch a useless pair.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256)
 k_row_window(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __restrict__ Acol,
              const int32_t* __restrict__ Brp, const int32_t* __restrict__ Bcol,
              int2* __restrict__ win, int32_t* __restrict__ list_small, int32_t* __restrict__ list_large,
-             int64_t* __restrict__ scalars)
+             unsigned* __restrict__ key_large, int64_t* __restrict__ scalars)
 {
     int row = rb + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (row >= re) return;
@@ -201,9 +203,11 @@ k_row_window(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __r
             atomicMax((long long*)&scalars[SC_MAXWIN], words);
             atomicMax((long long*)&scalars[SC_MAXP], (long long)P);
             atomicAdd((unsigned long long*)&scalars[SC_SUMP], P);
-            if ((long long)P > LARGE_P || ae - as > LARGE_LA)
-                list_large[atomicAdd((unsigned long long*)&scalars[SC_NLARGE1], 1ull)] = row;
-            else
+            if ((long long)P > LARGE_P || ae - as > LARGE_LA) {
+                const unsigned long long at = atomicAdd((unsigned long long*)&scalars[SC_NLARGE1], 1ull);
+                list_large[at] = row;
+                key_large[at] = ~(unsigned)min(P, 0xFFFFFFFFull);   // ascending sort = heaviest first
+            } else
                 list_small[atomicAdd((unsigned long long*)&scalars[SC_NSMALL1], 1ull)] = row;
         }
     }
@@ -223,13 +227,20 @@ k_step1_count(const int32_t* __restrict__ rows, int nrows_list, int rb,
               const int2* __restrict__ win, int keep_empty, int dcap_small,
               int64_t* __restrict__ D, int64_t* __restrict__ F,
               int32_t* __restrict__ list_small, int32_t* __restrict__ list_large,
-              int64_t* __restrict__ scalars)
+              unsigned* __restrict__ key_large, int64_t* __restrict__ scalars,
+              unsigned long long* __restrict__ work)
 {
     extern __shared__ unsigned sm[];
     __shared__ unsigned red[THREADS / 32 + 1];
     __shared__ Stage<THREADS> st;
+    __shared__ int s_li;
     const int tid = threadIdx.x;
-    for (int li = blockIdx.x; li < nrows_list; li += gridDim.x) {
+    for (;;) {                                      // rows are handed out through a work queue
+        if (tid == 0) s_li = (int)atomicAdd(work, 1ull);
+        __syncthreads();
+        const int li = s_li;
+        __syncthreads();
+        if (li >= nrows_list) break;
         const int row = rows[li];
         const int2 wnd = win[row - rb];
         const int base = wnd.x & ~31;
@@ -251,9 +262,11 @@ k_step1_count(const int32_t* __restrict__ rows, int nrows_list, int rb,
             D[row - rb] = d;
             F[row - rb] = f;
             atomicMax((long long*)&scalars[SC_MAXD], (long long)d);
-            if (THREADS == TH_LARGE || (int)d > dcap_small)
-                list_large[atomicAdd((unsigned long long*)&scalars[SC_NLARGE2], 1ull)] = row;
-            else
+            if (THREADS == TH_LARGE || (int)d > dcap_small) {
+                const unsigned long long at = atomicAdd((unsigned long long*)&scalars[SC_NLARGE2], 1ull);
+                list_large[at] = row;
+                key_large[at] = ~f;                                 // ascending sort = most pairs first
+            } else
                 list_small[atomicAdd((unsigned long long*)&scalars[SC_NSMALL2], 1ull)] = row;
         }
     }
@@ -276,7 +289,7 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
              const int64_t* __restrict__ c_row_ptr, const int64_t* __restrict__ pair_row_ptr,
              int32_t* __restrict__ c_tile_row, int32_t* __restrict__ c_tile_col,
              int64_t* __restrict__ pair_ptr, int2* __restrict__ pairs,
-             unsigned long long* __restrict__ prof)
+             unsigned long long* __restrict__ work, unsigned long long* __restrict__ prof)
 {
     extern __shared__ unsigned sm[];
     constexpr int NW = THREADS / 32;
@@ -290,8 +303,15 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
     unsigned* prefix = sm + Wmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long tprev = prof ? clock64() : 0;
+    const long long tstart = tprev;
+    __shared__ int s_li;
 #define PROF_MARK(i) do { if (prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prof[i], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
-    for (int li = blockIdx.x; li < nrows_list; li += gridDim.x) {
+    for (;;) {                                      // rows are handed out through a work queue
+        if (tid == 0) s_li = (int)atomicAdd(work, 1ull);
+        __syncthreads();
+        const int li = s_li;
+        __syncthreads();
+        if (li >= nrows_list) break;
         const int row = rows[li];
         const int64_t cbase = c_row_ptr[row - rb];
         const int D = (int)(c_row_ptr[row - rb + 1] - cbase);
@@ -470,6 +490,7 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
         }
         PROF_MARK(6);
     }
+    if (prof && tid == 0) atomicMax(&prof[7], (unsigned long long)(clock64() - tstart));
 #undef PROF_MARK
 }
 
@@ -491,7 +512,9 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     const int nrows = re - rb;
     int64_t* pair_row_ptr = nullptr;
     int2* win = nullptr;
-    int32_t *l1s = nullptr, *l1l = nullptr, *l2s = nullptr, *l2l = nullptr;
+    int32_t *l1s = nullptr, *l1l = nullptr, *l2s = nullptr, *l2l = nullptr, *lsorted = nullptr;
+    unsigned *key_l = nullptr, *key_sorted = nullptr;
+    char* sort_tmp = nullptr;
     int2* tmp_pq = nullptr;
     int32_t* tmp_j = nullptr;
     unsigned* gscr = nullptr;
@@ -499,6 +522,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     auto cleanup_tmp = [&]() {
         pem_free(ctx, pair_row_ptr); pem_free(ctx, win); pem_free(ctx, l1s); pem_free(ctx, l1l);
         pem_free(ctx, l2s); pem_free(ctx, l2l); pem_free(ctx, gscr); pem_free(ctx, prof);
+        pem_free(ctx, lsorted); pem_free(ctx, key_l); pem_free(ctx, key_sorted); pem_free(ctx, sort_tmp);
         pem_free(ctx, tmp_pq); pem_free(ctx, tmp_j);
     };
     auto fail = [&](int rc) { cleanup_tmp(); pem_result_free(ctx, C); return rc; };
@@ -509,6 +533,21 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     S_TRY(pem_alloc(ctx, &win, (size_t)nrows));
     S_TRY(pem_alloc(ctx, &l1s, (size_t)nrows)); S_TRY(pem_alloc(ctx, &l1l, (size_t)nrows));
     S_TRY(pem_alloc(ctx, &l2s, (size_t)nrows)); S_TRY(pem_alloc(ctx, &l2l, (size_t)nrows));
+    S_TRY(pem_alloc(ctx, &lsorted, (size_t)nrows));
+    S_TRY(pem_alloc(ctx, &key_l, (size_t)nrows)); S_TRY(pem_alloc(ctx, &key_sorted, (size_t)nrows));
+    size_t sort_bytes = 0;
+    S_CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_l, key_sorted, l1l, lsorted, nrows > 0 ? nrows : 1, 0, 32, ctx->stream));
+    S_TRY(pem_alloc(ctx, &sort_tmp, sort_bytes));
+    unsigned long long* work = (unsigned long long*)(ctx->d_scalars + SC_WORK0);
+    // heavy rows are taken from the work queue heaviest first (longest-processing-time order)
+    auto sort_heavy = [&](int32_t*& list, int64_t n) -> int {
+        if (n < 2) return PEM_OK;
+        size_t b = sort_bytes;
+        PEM_CK(cub::DeviceRadixSort::SortPairs(sort_tmp, b, key_l, key_sorted, list, lsorted, (int)n, 0, 32, ctx->stream));
+        ctx->launches += 3;
+        std::swap(list, lsorted);
+        return PEM_OK;
+    };
     S_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
     S_CK(cudaMemsetAsync(C->row_ptr, 0, ((size_t)nrows + 1) * 8, ctx->stream));
     S_CK(cudaMemsetAsync(pair_row_ptr, 0, ((size_t)nrows + 1) * 8, ctx->stream));
@@ -517,7 +556,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     int64_t maxwin = 0, maxd = 0, n1s = 0, n1l = 0, n2s = 0, n2l = 0;
     if (any) {
         k_row_window<<<pem_div_up((int64_t)nrows * 32, 256), 256, 0, ctx->stream>>>(
-            rb, re, A->tile_row_ptr, A->tile_col_idx, B->tile_row_ptr, B->tile_col_idx, win, l1s, l1l, ctx->d_scalars);
+            rb, re, A->tile_row_ptr, A->tile_col_idx, B->tile_row_ptr, B->tile_col_idx, win, l1s, l1l, key_l, ctx->d_scalars);
         ++ctx->launches;
         S_CK(cudaGetLastError());
         S_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -546,11 +585,12 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     if (n1s + n1l > 0) {
         S_CK(cudaFuncSetAttribute(k_step1_count<TH_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
         S_CK(cudaFuncSetAttribute(k_step1_count<TH_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
+        S_TRY(sort_heavy(l1l, n1l));
         if (n1l > 0) {  // heavy rows first: they are the tail
             int grid = (int)std::min<int64_t>(n1l, (int64_t)ctx->sm_count * 2);
             k_step1_count<TH_LARGE><<<grid, TH_LARGE, win_bytes, ctx->stream>>>(
                 l1l, (int)n1l, rb, A->tile_row_ptr, A->tile_col_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx,
-                B->row_occ, win, ctx->opt_keep_empty, dcap_small, C->row_ptr, pair_row_ptr, l2s, l2l, ctx->d_scalars);
+                B->row_occ, win, ctx->opt_keep_empty, dcap_small, C->row_ptr, pair_row_ptr, l2s, l2l, key_l, ctx->d_scalars, work + 0);
             ++ctx->launches;
             S_CK(cudaGetLastError());
         }
@@ -558,7 +598,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
             int grid = (int)std::min<int64_t>(n1s, (int64_t)ctx->sm_count * 16);
             k_step1_count<TH_SMALL><<<grid, TH_SMALL, win_bytes, ctx->stream>>>(
                 l1s, (int)n1s, rb, A->tile_row_ptr, A->tile_col_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx,
-                B->row_occ, win, ctx->opt_keep_empty, dcap_small, C->row_ptr, pair_row_ptr, l2s, l2l, ctx->d_scalars);
+                B->row_occ, win, ctx->opt_keep_empty, dcap_small, C->row_ptr, pair_row_ptr, l2s, l2l, key_l, ctx->d_scalars, work + 1);
             ++ctx->launches;
             S_CK(cudaGetLastError());
         }
@@ -591,10 +631,11 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
         PEM_CK(cudaMemcpyAsync(h, prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         PEM_CK(cudaStreamSynchronize(ctx->stream));
         fprintf(stderr, "[step1 %s: cycles summed over %d blocks] passA %llu scanW %llu passB %llu scanD %llu emit %llu "
-                        "passC %llu passD %llu\n", which, grid, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+                        "passC %llu passD %llu | slowest block %llu cycles\n", which, grid, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
         PEM_CK(cudaMemsetAsync(prof, 0, 16 * 8, ctx->stream));
         return PEM_OK;
     };
+    S_TRY(sort_heavy(l2l, n2l));
     if (n2l > 0) {
         const bool two_per_sm = 2 * (smem_fill_large + static_large) <= budget;
         int grid = (int)std::min<int64_t>(n2l, (int64_t)ctx->sm_count * (two_per_sm ? 2 : 1));
@@ -607,7 +648,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
         k_step1_fill<TH_LARGE><<<grid, TH_LARGE, smem_fill_large, ctx->stream>>>(
             l2l, (int)n2l, rb, A->tile_row_ptr, A->tile_col_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx, B->row_occ,
             win, ctx->opt_keep_empty, (int)maxwin, dcap_large, gscr, stride, tmp_pq, tmp_j, C->row_ptr, pair_row_ptr,
-            C->tile_row, C->tile_col, C->pair_ptr, C->pair_list, prof);
+            C->tile_row, C->tile_col, C->pair_ptr, C->pair_list, work + 2, prof);
         ++ctx->launches;
         S_CK(cudaGetLastError());
         if (want_prof) S_TRY(report("fill<1024>", grid));
@@ -618,7 +659,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
         k_step1_fill<TH_SMALL><<<grid, TH_SMALL, smem_fill_small, ctx->stream>>>(
             l2s, (int)n2s, rb, A->tile_row_ptr, A->tile_col_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx, B->row_occ,
             win, ctx->opt_keep_empty, (int)maxwin, dcap_small, nullptr, 0, tmp_pq, tmp_j, C->row_ptr, pair_row_ptr,
-            C->tile_row, C->tile_col, C->pair_ptr, C->pair_list, prof);
+            C->tile_row, C->tile_col, C->pair_ptr, C->pair_list, work + 3, prof);
         ++ctx->launches;
         S_CK(cudaGetLastError());
         if (want_prof) S_TRY(report("fill<128>", grid));

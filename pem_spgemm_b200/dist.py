@@ -1,0 +1,65 @@
+"""Multi-GPU sharding of C = A*B: the host-side logic around the engine's panel entry points.
+
+The path shards by independent units: every tile row of C depends only on the same tile row of A
+and on (read-only, replicated) B.  A is cut into contiguous tile-row panels with balanced flop
+(`pem_partition_panels`, device-side flop count), each rank multiplies its panel with
+`pem_spgemm_panel`, and the ONLY exchange is an all-gather of three integers per rank
+{nnz(C shard), C' tiles, pairs}, whose exclusive scan gives every shard's offset in the global C
+(north_star: "NCCL used only to gather per-shard C nnz and offsets").  The reference has no
+multi-GPU code.
+
+Works with any torch.distributed backend: NCCL on the GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class ShardLayout:
+    rank: int
+    world: int
+    sizes: np.ndarray      # int64[world, 3]: nnz, tiles, pairs of every shard
+    offsets: np.ndarray    # int64[world, 3]: exclusive scan over ranks (this shard's start in global C)
+    totals: np.ndarray     # int64[3]
+
+    @property
+    def nnz_offset(self) -> int:
+        return int(self.offsets[self.rank, 0])
+
+
+def layout_from_sizes(sizes: np.ndarray, rank: int) -> ShardLayout:
+    sizes = np.asarray(sizes, np.int64).reshape(-1, 3)
+    offsets = np.cumsum(sizes, axis=0) - sizes
+    return ShardLayout(rank, sizes.shape[0], sizes, offsets, sizes.sum(axis=0))
+
+
+def exchange_shard_sizes(nnz: int, tiles: int, pairs: int, device=None) -> ShardLayout:
+    """All-gather this rank's {nnz, tiles, pairs}; returns every shard's sizes and global offsets.
+    Without an initialised process group this is the single-shard layout."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return layout_from_sizes(np.array([[nnz, tiles, pairs]], np.int64), 0)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.tensor([nnz, tiles, pairs], dtype=torch.int64, device=device)
+    allsz = torch.empty(world * 3, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allsz, mine)
+    return layout_from_sizes(allsz.cpu().numpy(), rank)
+
+
+def split_by_weight(weights: np.ndarray, nparts: int) -> np.ndarray:
+    """Host restatement of pem_partition_panels' rule, for tests and for hosts that already hold the
+    per-tile-row flop counts: contiguous panels, panel p closes at the first row where the running
+    weight (each row counted as weight+1) reaches p/nparts of the total."""
+    w = np.asarray(weights, np.int64) + 1
+    total = int(w.sum())
+    run = np.cumsum(w)
+    bounds = np.zeros(nparts + 1, np.int32)
+    bounds[nparts] = w.size
+    for p in range(1, nparts):
+        # first r with run[r] * nparts >= total * p
+        bounds[p] = min(int(np.searchsorted(run * nparts, total * p, side="left")) + 1, w.size)
+    return np.maximum.accumulate(bounds)

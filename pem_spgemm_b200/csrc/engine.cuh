@@ -144,3 +144,4 @@ enum {
 // step entry points implemented in spgemm.cu / convert.cu / export.cu
 int pem_scan_exclusive_i64(pem_ctx* ctx, int64_t* d_inout, int64_t n);  // in place, n elements
 extern "C" int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C);
+int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C);  // step1_esc.cu

@@ -510,6 +510,14 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     pem_result* C = new pem_result();
     C->rb = rb; C->re = re; C->rows = A->rows; C->cols = B->cols; C->tile_cols = B->tile_cols;
     const int nrows = re - rb;
+    if (ctx->opt_step1_path != 1) {     // default: expand-sort-compress (step1_esc.cu)
+        int rc = pem_alloc(ctx, &C->row_ptr, (size_t)nrows + 1);
+        if (rc == PEM_OK) rc = pem_step1_esc(ctx, A, B, C);
+        if (rc != PEM_OK) { pem_result_free(ctx, C); return rc; }
+        C->stage = 1;
+        *out = C;
+        return PEM_OK;
+    }
     int64_t* pair_row_ptr = nullptr;
     int2* win = nullptr;
     int32_t *l1s = nullptr, *l1l = nullptr, *l2s = nullptr, *l2l = nullptr, *lsorted = nullptr;

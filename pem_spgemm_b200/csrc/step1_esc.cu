@@ -1,0 +1,445 @@
+// Step 1, default path: tile-level symbolic SpGEMM by EXPAND - SORT - COMPRESS.
+//
+// Replaces, in /root/reference: tile_spgemm_step1_cuda_spa_kernel / ..._numeric_... (spgemm.cu:
+// 271-384), the NSPARSE hash path chosen by `B_tileCols > 512*32` (spgemm.cu:1142,
+// NSPARSE/spgemm_nsparse_kernel.h:1171-1438) and the CSC pair search
+// pem_spgemm_step2_search_pairs (spgemm.cu:387-497).  Output contract as step1.cu: C' in CSR+COO
+// with ascending tile columns, and per C' tile the (A tile, B tile) pairs in ascending k.
+//
+// The per-row accumulators of the reference (a 2 KB bitmap per warp, or hash tables binned by row
+// length) serialise on hub rows: one tile row of a power-law matrix can own a third of all tile
+// products.  Here the unit of work is the TILE PRODUCT, not the row:
+//
+//   products  k_tile_products: thread per A tile p: len(p) = |B' row of p's tile column|, and the
+//             tile-column window [jmin, jmax] of every C' row (atomicMin/Max).  Exclusive scan of
+//             len -> product index space [0, P).
+//   split     k_merge_split: merge-path partition of (A tiles, products) into chunks of CHUNK
+//             work items, so a block sees at most CHUNK tiles AND at most CHUNK products whatever
+//             the row-length distribution (hub rows are cut across thousands of blocks).
+//   expand    k_expand: a block stages its A-tile slice (product offsets, first B tile, column
+//             occupancy, row) in shared memory; lanes take products warp-striped (coalesced 2-byte
+//             rowOcc loads, 8 independent loads in flight per lane) and keep product (p, q) iff
+//             colOcc(p) & rowOcc(q) != 0, i.e. iff the 16x16 boolean product of the two tiles is
+//             non-empty.  Kept products are written in product order (ballot/popc ranks inside a
+//             warp, a block scan across warps) as key = (C' row, tile column - jmin(row)),
+//             value = (p, q).
+//   compact   blocks wrote at their product base; k_compact closes the holes.
+//   sort      ONE stable LSD radix sort of (key, value) over exactly the key bits in use.  Products
+//             were emitted in ascending p, and p ascends with (row, k), so after a stable sort by
+//             (row, column) every C' tile's pairs are contiguous and already in ascending k: the
+//             order step 3 needs for bit-reproducible sums.
+//   compress  heads of equal-key runs = C' tiles (stream compaction of run starts = pair_ptr);
+//             k_ctiles decodes (row, col) and builds the CSR row pointer.
+// No per-row shared-memory structure exists, so there is no limit on B's tile-column count and
+// no long-row special case.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <climits>
+
+#include "engine.cuh"
+
+namespace {
+
+constexpr int EX_THREADS = 256;
+constexpr int EX_ITEMS = 8;                       // products per lane
+constexpr int EX_CHUNK = EX_THREADS * EX_ITEMS;   // work items (A tiles + products) per block
+constexpr int EX_WARPS = EX_THREADS / 32;
+
+// thread per A tile of the panel
+__global__ void __launch_bounds__(256)
+k_tile_products(int p0, int np, int rb, const int32_t* __restrict__ Acol, const int32_t* __restrict__ Arow,
+                const int32_t* __restrict__ Brp, const int32_t* __restrict__ Bcol,
+                int64_t* __restrict__ plen, int32_t* __restrict__ bfirst, int* __restrict__ jmin,
+                int* __restrict__ jmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > np) return;
+    if (i == np) { plen[i] = 0; return; }
+    const int p = p0 + i;
+    const int k = Acol[p];
+    const int bs = Brp[k], be = Brp[k + 1];
+    plen[i] = be - bs;
+    bfirst[i] = bs;
+    if (be > bs) {
+        const int row = Arow[p] - rb;
+        const int lo = Bcol[bs], hi = Bcol[be - 1];
+        if (lo < jmin[row]) atomicMin(&jmin[row], lo);
+        if (hi > jmax[row]) atomicMax(&jmax[row], hi);
+    }
+}
+
+// widest window over the panel's rows -> scalars[SC_MAXWIN]; total products -> scalars[SC_SUMP]
+__global__ void __launch_bounds__(256)
+k_max_window(int nrows, const int* __restrict__ jmin, const int* __restrict__ jmax,
+             const int64_t* __restrict__ pptr, int np, int64_t* __restrict__ scalars)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int w = 0;
+    if (r < nrows && jmax[r] >= jmin[r]) w = jmax[r] - jmin[r] + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((threadIdx.x & 31) == 0 && w > 0) atomicMax((long long*)&scalars[SC_MAXWIN], (long long)w);
+    if (r == 0) scalars[SC_SUMP] = pptr[np];
+}
+
+// merge-path split: chunk b starts at diagonal d = b*CHUNK of the (A tile, product) grid; split[b] =
+// number of A tiles wholly consumed before it (the chunk's first product is d - split[b])
+__global__ void __launch_bounds__(256)
+k_merge_split(int nchunks, int np, int64_t P, const int64_t* __restrict__ pptr, int32_t* __restrict__ split)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nchunks) return;
+    const int64_t d = min((int64_t)b * EX_CHUNK, (int64_t)np + P);
+    int64_t lo = max((int64_t)0, d - P), hi = min(d, (int64_t)np);
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (pptr[mid + 1] <= d - mid - 1) lo = mid + 1; else hi = mid;
+    }
+    split[b] = (int32_t)lo;
+}
+
+// MODE 0: count kept products per chunk.  MODE 1: also write them (at out_base[b], or at the chunk's
+// first product index when out_base is null).
+template <class KeyT, int MODE>
+__global__ void __launch_bounds__(EX_THREADS)
+k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, const int32_t* __restrict__ split,
+         const int32_t* __restrict__ bfirst, const uint16_t* __restrict__ AcolOcc,
+         const int32_t* __restrict__ Arow, const int32_t* __restrict__ Bcol,
+         const uint16_t* __restrict__ BrowOcc, const int* __restrict__ jmin, int wbits, int keep_empty,
+         const int64_t* __restrict__ out_base, int64_t* __restrict__ chunk_cnt,
+         KeyT* __restrict__ out_key, int2* __restrict__ out_val)
+{
+    __shared__ int s_rel[EX_CHUNK + 2];       // product offset of slice tile t, relative to the chunk's first product
+    __shared__ unsigned s_q0[EX_CHUNK + 1];   // first B tile of tile t's B' row, minus s_rel[t] (mod 2^32)
+    __shared__ unsigned short s_occ[EX_CHUNK + 1];
+    __shared__ unsigned s_wcnt[EX_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t total = (int64_t)np + P;
+    const int64_t d0 = (int64_t)blockIdx.x * EX_CHUNK, d1 = min(d0 + EX_CHUNK, total);
+    const int i0 = split[blockIdx.x], i1 = split[blockIdx.x + 1];
+    const int64_t j0 = d0 - i0, j1 = d1 - i1;           // products [j0, j1)
+    const int nprod = (int)(j1 - j0);
+    const int nt = min(i1 + 1, np) - i0;                // slice tiles [i0, i0 + nt)
+    for (int t = tid; t <= nt; t += EX_THREADS) {
+        const int64_t rel = pptr[i0 + t] - j0;
+        const int r = (int)min(max(rel, (int64_t)INT_MIN), (int64_t)INT_MAX);
+        s_rel[t] = r;
+        if (t < nt) {
+            s_q0[t] = (unsigned)bfirst[i0 + t] - (unsigned)r;
+            s_occ[t] = keep_empty ? (unsigned short)0xFFFFu : AcolOcc[p0 + i0 + t];
+        }
+    }
+    __syncthreads();
+    // lane's products: g = wbase + u*32 + lane (relative to j0)
+    const int wbase = warp * (32 * EX_ITEMS);
+    int tq[EX_ITEMS];                          // slice tile of item u
+    int qq[EX_ITEMS];                          // B tile of item u (-1: none)
+    int t = 0;
+    {
+        const int g = wbase + lane;
+        if (g < nprod) {                       // last t in [0, nt) with s_rel[t] <= g
+            int lo = 0, hi = nt - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_rel[mid] <= g) lo = mid; else hi = mid - 1;
+            }
+            t = lo;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EX_ITEMS; ++u) {
+        const int g = wbase + u * 32 + lane;
+        qq[u] = -1;
+        tq[u] = 0;
+        if (g < nprod) {
+            while (s_rel[t + 1] <= g) ++t;     // s_rel[nt] >= nprod ends the walk
+            tq[u] = t;
+            qq[u] = (int)(s_q0[t] + (unsigned)g);
+        }
+    }
+    unsigned occ[EX_ITEMS];
+#pragma unroll
+    for (int u = 0; u < EX_ITEMS; ++u) occ[u] = qq[u] >= 0 ? (unsigned)BrowOcc[qq[u]] : 0u;
+    unsigned keepbits = 0, mine = 0;
+#pragma unroll
+    for (int u = 0; u < EX_ITEMS; ++u) {
+        const bool keep = qq[u] >= 0 && (occ[u] & s_occ[tq[u]]) != 0;
+        keepbits |= (unsigned)keep << u;
+        mine += keep;
+    }
+    unsigned wsum = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if (lane == 0) s_wcnt[warp] = wsum;
+    __syncthreads();
+    unsigned before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < EX_WARPS; ++w) {
+        const unsigned c = s_wcnt[w];
+        before += w < warp ? c : 0u;
+        all += c;
+    }
+    if (tid == 0 && chunk_cnt) chunk_cnt[blockIdx.x] = all;
+    if (MODE == 0) return;
+    int64_t pos = (out_base ? out_base[blockIdx.x] : j0) + before;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int u = 0; u < EX_ITEMS; ++u) {
+        const bool keep = (keepbits >> u) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int64_t at = pos + __popc(bal & lt);
+            const int p = p0 + i0 + tq[u];
+            const int row = Arow[p] - rb;
+            const int j = Bcol[qq[u]];
+            out_key[at] = ((KeyT)(unsigned)row << wbits) | (KeyT)(unsigned)(j - jmin[row]);
+            out_val[at] = make_int2(p, qq[u]);
+        }
+        pos += __popc(bal);
+    }
+}
+
+// close the holes between the chunks' outputs (written at their product bases)
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+k_compact(const int32_t* __restrict__ split, const int64_t* __restrict__ chunk_off,
+          const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
+          KeyT* __restrict__ out_key, int2* __restrict__ out_val)
+{
+    const int64_t src = (int64_t)blockIdx.x * EX_CHUNK - split[blockIdx.x];
+    const int64_t dst = chunk_off[blockIdx.x];
+    const int n = (int)(chunk_off[blockIdx.x + 1] - dst);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        out_key[dst + i] = in_key[src + i];
+        out_val[dst + i] = in_val[src + i];
+    }
+}
+
+template <class KeyT>
+struct RunHead {
+    const KeyT* keys;
+    __device__ __forceinline__ bool operator()(int64_t i) const { return i == 0 || keys[i] != keys[i - 1]; }
+};
+
+// thread per C' tile: decode the run's key, open the CSR rows it starts
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+k_ctiles(int64_t ntiles, int64_t npairs, int nrows, int rb, int wbits, const KeyT* __restrict__ keys,
+         const int64_t* __restrict__ heads, const int* __restrict__ jmin, int64_t* __restrict__ pair_ptr,
+         int32_t* __restrict__ tile_row, int32_t* __restrict__ tile_col, int64_t* __restrict__ row_ptr)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int64_t h = heads[t];
+    const KeyT key = keys[h];
+    const int row = (int)(key >> wbits);
+    const int jrel = (int)(key & (((KeyT)1 << wbits) - 1));
+    pair_ptr[t] = h;
+    tile_row[t] = rb + row;
+    tile_col[t] = jmin[row] + jrel;
+    const int prev = t ? (int)(keys[heads[t - 1]] >> wbits) : -1;
+    for (int r = prev + 1; r <= row; ++r) row_ptr[r] = t;
+    if (t == ntiles - 1) {
+        for (int r = row + 1; r <= nrows; ++r) row_ptr[r] = ntiles;
+        pair_ptr[ntiles] = npairs;
+    }
+}
+
+__global__ void k_fill_i32(int* p, int n, int v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+inline int h_bits(int64_t n)
+{  // bits needed for values 0..n-1 (at least 1)
+    int b = 1;
+    while ((int64_t(1) << b) < n) ++b;
+    return b;
+}
+
+template <class KeyT>
+int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C, int p0, int np, int64_t P,
+            int wbits, int rbits, const int64_t* pptr, const int32_t* bfirst, const int* jmin)
+{
+    const int nrows = C->re - C->rb, rb = C->rb;
+    const int64_t total = (int64_t)np + P;
+    const int64_t nchunks64 = (total + EX_CHUNK - 1) / EX_CHUNK;
+    if (nchunks64 > 0x7ffffff0LL) return ctx->fail(PEM_ERR_LIMIT, "step 1: more than 2^42 tile products");
+    const int nchunks = (int)nchunks64;
+    int32_t* split = nullptr;
+    int64_t* chunk_off = nullptr;
+    KeyT *key_a = nullptr, *key_b = nullptr;
+    int2 *val_a = nullptr, *val_b = nullptr;
+    char* tmp = nullptr;
+    int64_t* heads = nullptr;
+    auto cleanup = [&]() {
+        pem_free(ctx, split); pem_free(ctx, chunk_off); pem_free(ctx, key_a); pem_free(ctx, key_b);
+        pem_free(ctx, val_a); pem_free(ctx, val_b); pem_free(ctx, tmp); pem_free(ctx, heads);
+    };
+#define E_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) { cleanup(); return rc_; } } while (0)
+#define E_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return ctx->fail_cuda(e_, #call, __FILE__, __LINE__); } } while (0)
+#define E_LAUNCHED() do { ++ctx->launches; E_CK(cudaGetLastError()); } while (0)
+    E_TRY(pem_alloc(ctx, &split, (size_t)nchunks + 1));
+    E_TRY(pem_alloc(ctx, &chunk_off, (size_t)nchunks + 1));
+    k_merge_split<<<pem_div_up((int64_t)nchunks + 1, 256), 256, 0, ctx->stream>>>(nchunks, np, P, pptr, split);
+    E_LAUNCHED();
+
+    // Staged layout (one expansion): chunks write at their product base into P-sized buffers, then
+    // the holes are closed.  When P-sized buffers would be too large, count first and write exactly.
+    size_t free_b = 0, total_b = 0;
+    E_CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t staged_bytes = (size_t)P * (sizeof(KeyT) + sizeof(int2));
+    const bool staged = staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
+    int64_t F = 0;
+    if (staged) {
+        E_TRY(pem_alloc(ctx, &key_b, (size_t)P));
+        E_TRY(pem_alloc(ctx, &val_b, (size_t)P));
+        k_expand<KeyT, 1><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+            np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
+            ctx->opt_keep_empty, nullptr, chunk_off, key_b, val_b);
+        E_LAUNCHED();
+    } else {
+        k_expand<KeyT, 0><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+            np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
+            ctx->opt_keep_empty, nullptr, chunk_off, nullptr, nullptr);
+        E_LAUNCHED();
+    }
+    E_CK(cudaMemsetAsync(chunk_off + nchunks, 0, 8, ctx->stream));
+    E_TRY(pem_scan_exclusive_i64(ctx, chunk_off, (int64_t)nchunks + 1));
+    E_CK(cudaMemcpyAsync(ctx->h_scalars, chunk_off + nchunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    E_CK(cudaStreamSynchronize(ctx->stream));
+    F = ctx->h_scalars[0];
+    C->pairs = F;
+    if (F == 0) {
+        cleanup();
+        return PEM_OK;
+    }
+    E_TRY(pem_alloc(ctx, &key_a, (size_t)F));
+    E_TRY(pem_alloc(ctx, &val_a, (size_t)F));
+    if (staged) {
+        k_compact<KeyT><<<nchunks, 256, 0, ctx->stream>>>(split, chunk_off, key_b, val_b, key_a, val_a);
+        E_LAUNCHED();
+        pem_free(ctx, key_b);
+        pem_free(ctx, val_b);
+    } else {
+        k_expand<KeyT, 1><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+            np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
+            ctx->opt_keep_empty, chunk_off, nullptr, key_a, val_a);
+        E_LAUNCHED();
+    }
+    // stable radix sort by (row, column) over the bits in use
+    E_TRY(pem_alloc(ctx, &key_b, (size_t)F));
+    E_TRY(pem_alloc(ctx, &val_b, (size_t)F));
+    {
+        cub::DoubleBuffer<KeyT> dk(key_a, key_b);
+        cub::DoubleBuffer<unsigned long long> dv((unsigned long long*)val_a, (unsigned long long*)val_b);
+        size_t tb = 0;
+        E_CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, F, 0, wbits + rbits, ctx->stream));
+        E_TRY(pem_alloc(ctx, &tmp, tb));
+        E_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, F, 0, wbits + rbits, ctx->stream));
+        ctx->launches += 2 + (wbits + rbits + 7) / 8;
+        pem_free(ctx, tmp);
+        if (dk.Current() != key_a) { std::swap(key_a, key_b); std::swap(val_a, val_b); }
+    }
+    pem_free(ctx, key_b);
+    pem_free(ctx, val_b);
+    // heads of the equal-key runs = C' tiles
+    E_TRY(pem_alloc(ctx, &heads, (size_t)F));
+    {
+        size_t tb = 0;
+        thrust::counting_iterator<int64_t> iota(0);
+        RunHead<KeyT> pred{key_a};
+        int64_t* d_n = ctx->d_scalars + SC_COUNT;
+        E_CK(cub::DeviceSelect::If(nullptr, tb, iota, heads, d_n, F, pred, ctx->stream));
+        E_TRY(pem_alloc(ctx, &tmp, tb));
+        E_CK(cub::DeviceSelect::If(tmp, tb, iota, heads, d_n, F, pred, ctx->stream));
+        ctx->launches += 2;
+        pem_free(ctx, tmp);
+        E_CK(cudaMemcpyAsync(ctx->h_scalars, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        E_CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const int64_t T = ctx->h_scalars[0];
+    C->tiles = T;
+    pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col); pem_free(ctx, C->pair_ptr);
+    E_TRY(pem_alloc(ctx, &C->tile_row, (size_t)T));
+    E_TRY(pem_alloc(ctx, &C->tile_col, (size_t)T));
+    E_TRY(pem_alloc(ctx, &C->pair_ptr, (size_t)T + 1));
+    k_ctiles<KeyT><<<pem_div_up(T, 256), 256, 0, ctx->stream>>>(T, F, nrows, rb, wbits, key_a, heads, jmin, C->pair_ptr,
+                                                                C->tile_row, C->tile_col, C->row_ptr);
+    E_LAUNCHED();
+    C->pair_list = val_a;
+    val_a = nullptr;
+    cleanup();
+#undef E_TRY
+#undef E_CK
+#undef E_LAUNCHED
+    return PEM_OK;
+}
+
+}  // namespace
+
+// called by pem_step1_symbolic (step1.cu) with a fresh result whose row_ptr is allocated
+int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
+{
+    const int rb = C->rb, re = C->re, nrows = re - rb;
+    PEM_CK(cudaMemsetAsync(C->row_ptr, 0, ((size_t)nrows + 1) * 8, ctx->stream));
+    PEM_TRY(pem_alloc(ctx, &C->tile_row, 0));
+    PEM_TRY(pem_alloc(ctx, &C->tile_col, 0));
+    PEM_TRY(pem_alloc(ctx, &C->pair_ptr, 1));
+    PEM_CK(cudaMemsetAsync(C->pair_ptr, 0, 8, ctx->stream));
+    if (nrows == 0 || A->tiles == 0 || B->tiles == 0) return PEM_OK;
+    // A tiles of the panel
+    int p0 = 0, p1 = A->tiles;
+    if (rb != 0 || re != A->tile_rows) {
+        int32_t h[2];
+        PEM_CK(cudaMemcpyAsync(&h[0], A->tile_row_ptr + rb, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PEM_CK(cudaMemcpyAsync(&h[1], A->tile_row_ptr + re, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PEM_CK(cudaStreamSynchronize(ctx->stream));
+        p0 = h[0]; p1 = h[1];
+    }
+    const int np = p1 - p0;
+    if (np == 0) return PEM_OK;
+    int64_t* pptr = nullptr;
+    int32_t* bfirst = nullptr;
+    int *jmin = nullptr, *jmax = nullptr;
+    auto cleanup = [&]() { pem_free(ctx, pptr); pem_free(ctx, bfirst); pem_free(ctx, jmin); pem_free(ctx, jmax); };
+#define E_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) { cleanup(); return rc_; } } while (0)
+#define E_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return ctx->fail_cuda(e_, #call, __FILE__, __LINE__); } } while (0)
+    E_TRY(pem_alloc(ctx, &pptr, (size_t)np + 1));
+    E_TRY(pem_alloc(ctx, &bfirst, (size_t)np));
+    E_TRY(pem_alloc(ctx, &jmin, (size_t)nrows));
+    E_TRY(pem_alloc(ctx, &jmax, (size_t)nrows));
+    E_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
+    k_fill_i32<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(jmin, nrows, INT_MAX);
+    ++ctx->launches;
+    E_CK(cudaMemsetAsync(jmax, 0xFF, (size_t)nrows * 4, ctx->stream));   // -1
+    k_tile_products<<<pem_div_up((int64_t)np + 1, 256), 256, 0, ctx->stream>>>(
+        p0, np, rb, A->tile_col_idx, A->tile_row_idx, B->tile_row_ptr, B->tile_col_idx, pptr, bfirst, jmin, jmax);
+    ++ctx->launches;
+    E_CK(cudaGetLastError());
+    E_TRY(pem_scan_exclusive_i64(ctx, pptr, (int64_t)np + 1));
+    k_max_window<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, jmin, jmax, pptr, np, ctx->d_scalars);
+    ++ctx->launches;
+    E_CK(cudaGetLastError());
+    E_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    E_CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t P = ctx->h_scalars[SC_SUMP];
+    const int64_t maxw = ctx->h_scalars[SC_MAXWIN];
+    C->tile_products = P;
+    int rc = PEM_OK;
+    if (P > 0) {
+        const int wbits = h_bits(maxw), rbits = h_bits(nrows);
+        if (wbits + rbits <= 32)
+            rc = esc_run<uint32_t>(ctx, A, B, C, p0, np, P, wbits, rbits, pptr, bfirst, jmin);
+        else
+            rc = esc_run<uint64_t>(ctx, A, B, C, p0, np, P, wbits, rbits, pptr, bfirst, jmin);
+    }
+#undef E_TRY
+#undef E_CK
+    cleanup();
+    return rc;
+}

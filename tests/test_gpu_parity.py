@@ -83,12 +83,14 @@ def test_conversion_input_errors(engine):
     A.free()
 
 
+@pytest.mark.parametrize("step1_path", [0, 1])     # 0: expand-sort-compress (default), 1: windowed bitmap SPA
 @pytest.mark.parametrize("keep_empty", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
-def test_steps_match_tile_oracle(engine, k, keep_empty):
+def test_steps_match_tile_oracle(engine, k, keep_empty, step1_path):
     """Step-by-step parity of C' structure, ordered pair lists, C masks and per-tile nnz."""
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
     engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep_empty)
+    engine.set_option(pem.OPT_STEP1_PATH, step1_path)
     try:
         A = engine.convert_coo(rows, cols, I, J, V)
         B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
@@ -119,6 +121,7 @@ def test_steps_match_tile_oracle(engine, k, keep_empty):
         C.free(); A.free(); B.free()
     finally:
         engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+        engine.set_option(pem.OPT_STEP1_PATH, 0)
 
 
 @pytest.mark.parametrize("shape,nnz,seed", SHAPES)
@@ -216,3 +219,25 @@ def test_row_owner_variant_is_bit_identical(engine, k):
     _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
     _assert_same_C(C1, oC)
     C0.free(); C1.free(); A.free(); B.free()
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_step1_paths_agree_at_full_size(engine, k):
+    """BASELINE.json sizes (too big for the numpy tile oracle): the two step-1 algorithms must
+    produce identical C' structure and pair lists, and step 3 identical value bits."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
+    C0 = engine.spgemm(A, B)
+    engine.set_option(pem.OPT_STEP1_PATH, 1)
+    try:
+        C1 = engine.spgemm(A, B)
+    finally:
+        engine.set_option(pem.OPT_STEP1_PATH, 0)
+    assert (C0.info.tiles, C0.info.pairs, C0.info.nnz) == (C1.info.tiles, C1.info.pairs, C1.info.nnz)
+    for name in ("row_ptr", "tile_row", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "tile_nnz_ptr", "vals"):
+        assert np.array_equal(C0.array(name), C1.array(name)), name
+    C0.free(); C1.free()
+    if B is not A:
+        B.free()
+    A.free()

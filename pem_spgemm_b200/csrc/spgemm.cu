@@ -6,6 +6,10 @@
 //           Atomic-free.
 //   step 3  numeric: one thread per C nonzero, ascending-k fma chain.  Replaces
 //           pem_spgemm_step3_accumulate (:593-661).  Atomic-free, C written exactly once.
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
 #include <climits>
 #include <chrono>
 #include <algorithm>
@@ -193,31 +197,73 @@ k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int
 }
 
 // =========================================================================================
-// Entry-owner variant of steps 2 and 3 (default): one thread per C' tile for the masks, one
-// thread per C NONZERO for the values.  Dense lane packing: every lane of every warp owns real
-// work, which is what wins on hypersparse tiles (1-3 nonzeros per tile).
+// Default mapping of steps 2 and 3.
+//   step 2: one thread per (A tile, B tile) PAIR.  The C tile mask is an OR over the tile's pairs,
+//           and OR is associative, so the pairs are the unit of work: no thread waits on a long
+//           pair list (hub tiles own thousands of pairs), every lane of every warp owns one 16x16
+//           boolean product.
+//   step 3: one thread per C NONZERO ("entry-owner", k_step3_entries) when C's tiles are sparse,
+//           one warp per C' tile (k_step3_tiles) when they are dense.
 // =========================================================================================
 
-// step 2, kernel 1 (tile-owner): as k_step2_masks, plus per pair which rows and columns of the C
-// tile the pair contributes to (pair_hit = rows << 16 | cols): the entry-owner step 3 uses it to
-// skip pairs that cannot touch a given entry.
-__global__ void __launch_bounds__(128)
-k_step2_masks_tile(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-                   const uint16_t* __restrict__ Amasks, const uint16_t* __restrict__ Bmasks,
-                   uint16_t* __restrict__ Cmasks, int64_t* __restrict__ c_tile_nnz, uint32_t* __restrict__ pair_hit)
+// first tile of every 256-pair step-2 block (every C' tile owns >= 1 pair, so a block overlaps
+// at most 257 tiles)
+constexpr int S2P_THREADS = 256;
+__global__ void __launch_bounds__(256)
+k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t* __restrict__ blk_tile)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
+    const int64_t s = pair_ptr[t], e = pair_ptr[t + 1];
+    for (int64_t b = (s + S2P_THREADS - 1) / S2P_THREADS; b * S2P_THREADS < e; ++b) blk_tile[b] = (int32_t)t;
+}
+
+// step 2, kernel 1 (pair-owner).  Lane = pair:
+//   prod[r] = OR over k in Amask[r] of Bmask[k]            (16x16 boolean product, 8 registers)
+//   hit     = (rows with prod != 0) << 16 | (OR of prod)    which C rows / columns the pair touches
+// The hit words of 32 consecutive pairs are bit-transposed with 32 ballots and stored as one
+// 32-word block: word 16+r (resp. c) of block b has bit i set iff pair 32b+i touches C row r
+// (resp. column c).  Step 3 ANDs two of those words to find the pairs feeding an entry (r, c)
+// without walking the list.
+// The products of a tile's pairs are OR-reduced by a segmented warp scan (pairs of a tile are
+// consecutive lanes); a run that lies inside one warp is stored, a run cut by a warp boundary is
+// merged with atomicOr into the zero-initialised mask array.
+__global__ void __launch_bounds__(S2P_THREADS)
+k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
+              const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+              const uint16_t* __restrict__ Amasks, const uint16_t* __restrict__ Bmasks,
+              uint32_t* __restrict__ Cmasks32, uint32_t* __restrict__ hit_t)
+{
+    __shared__ int s_ptr[S2P_THREADS + 2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t i0 = (int64_t)blockIdx.x * S2P_THREADS;
+    const int64_t t_lo = blk_tile[blockIdx.x];
+    const int64_t t_hi = (i0 + S2P_THREADS < n_pairs) ? (int64_t)blk_tile[blockIdx.x + 1] : n_tiles - 1;
+    const int span = (int)(t_hi - t_lo) + 1;
+    for (int x = tid; x <= span; x += S2P_THREADS) {
+        const int64_t rel = pair_ptr[t_lo + x] - i0;
+        s_ptr[x] = (int)max((int64_t)-0x40000000, min(rel, (int64_t)0x40000000));
+    }
+    __syncthreads();
+    const int64_t i = i0 + tid;
+    const bool valid = i < n_pairs;
+    int x = 0;
+    if (valid) {                                    // last x with s_ptr[x] <= tid
+        int lo = 0, hi = span - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_ptr[mid] <= tid) lo = mid; else hi = mid - 1;
+        }
+        x = lo;
+    }
+    const int seg_s = valid ? s_ptr[x] : tid, seg_e = valid ? s_ptr[x + 1] : tid + 1;   // run of this tile, block-relative
     unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int64_t ps = pair_ptr[t];
-    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
-    const int2* __restrict__ pl = pairs + ps;
-    uint32_t* __restrict__ hl = pair_hit + ps;
-    for (unsigned i = 0; i < np; ++i) {
-        const int2 ab = pl[i];
+    unsigned hit = 0;
+    if (valid) {
+        const int2 ab = pairs[i];
         const uint4* am4 = reinterpret_cast<const uint4*>(Amasks + (size_t)(unsigned)ab.x * 16u);
-        const uint4 x = am4[0], y = am4[1];
-        const unsigned aw[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        const uint4 ax = am4[0], ay = am4[1];
+        const unsigned aw[8] = {ax.x, ax.y, ax.z, ax.w, ay.x, ay.y, ay.z, ay.w};
         const uint16_t* __restrict__ bm = Bmasks + (size_t)(unsigned)ab.y * 16u;
         unsigned rows_hit = 0, cols_hit = 0;
 #pragma unroll
@@ -225,7 +271,7 @@ k_step2_masks_tile(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const 
             unsigned m = (aw[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
             unsigned o = 0;
             while (m) {
-                int k = __ffs(m) - 1;
+                const int k = __ffs(m) - 1;
                 m &= m - 1;
                 o |= bm[k];
             }
@@ -233,16 +279,53 @@ k_step2_masks_tile(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const 
             cols_hit |= o;
             rows_hit |= (o ? 1u : 0u) << r;
         }
-        hl[i] = (rows_hit << 16) | cols_hit;
+        hit = (rows_hit << 16) | cols_hit;
     }
-    uint4* out = reinterpret_cast<uint4*>(Cmasks + (size_t)t * 16);
-    out[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-    out[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
-    int nnz = 0;
+    // 32x32 bit transpose of the warp's hit words
+    unsigned mine = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) nnz += __popc(acc[i]);
-    c_tile_nnz[t] = nnz;
+    for (int b = 0; b < 32; ++b) {
+        const unsigned w = __ballot_sync(0xffffffffu, (hit >> b) & 1u);
+        mine = lane == b ? w : mine;
+    }
+    if (i0 + (tid & ~31) < n_pairs) hit_t[i0 + tid] = mine;
+    // segmented inclusive OR scan along the lanes of a tile's run
+    const int wfirst = tid & ~31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = lane >= o && tid - o >= seg_s;
+        if (!__any_sync(0xffffffffu, take)) break;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, acc[w], o);
+            acc[w] |= take ? v : 0u;
+        }
+    }
+    const bool tail = valid && (lane == 31 || tid + 1 >= seg_e);
+    if (tail) {
+        uint32_t* out = Cmasks32 + (size_t)(t_lo + x) * 8;
+        if (seg_s >= wfirst && seg_e <= wfirst + 32) {
+            reinterpret_cast<uint4*>(out)[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            reinterpret_cast<uint4*>(out)[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (acc[w]) atomicOr(&out[w], acc[w]);
+        }
+    }
 }
+
+// per-tile nnz = popcount of the 256-bit mask, fed straight into the exclusive scan
+struct TileNnz {
+    const uint4* masks;
+    int64_t n_tiles;
+    __device__ __forceinline__ int64_t operator()(int64_t t) const
+    {
+        if (t >= n_tiles) return 0;
+        const uint4 a = masks[2 * t], b = masks[2 * t + 1];
+        return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+    }
+};
 
 // first tile of every entry-owner step-3 block (a tile holds <= 256 = S3E_ENTRIES nonzeros, so it
 // covers at most one block boundary)
@@ -271,7 +354,7 @@ __global__ void __launch_bounds__(S3E_ENTRIES)
 k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
                 const int64_t* __restrict__ c_tile_nnz_ptr, const uint8_t* __restrict__ row_col_idx,
                 const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-                const uint32_t* __restrict__ pair_hit,
+                const uint32_t* __restrict__ hit_t,
                 const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
                 const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
                 const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
@@ -309,31 +392,31 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
     const unsigned rc = row_col_idx[n];
     const unsigned r = rc >> 4, c = rc & 15u;
     const unsigned below_c = (1u << c) - 1u;
-    const unsigned want = (0x10000u << r) | (1u << c);
-    const int64_t ps = pair_ptr[t];
-    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
-    const int2* __restrict__ pl = pairs + ps;
-    const uint32_t* __restrict__ hl = pair_hit + ps;
+    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
     double acc = 0.0;
-    unsigned i = 0;
-    for (;;) {
-        while (i < np && (hl[i] & want) != want) ++i;       // cheap skip loop
-        if (i >= np) break;
-        const int2 ab = pl[i];
-        ++i;
-        const unsigned ia = (unsigned)ab.x * 16u, ib = (unsigned)ab.y * 16u;
-        const unsigned am = A_masks[ia + r];
-        unsigned m = am & B_masks_t[ib + c];
-        if (m) {
-            const double* __restrict__ av = A_vals + (A_off[ab.x] + A_rowptr[ia + r]);
-            const double* __restrict__ bv = B_vals + B_off[ab.y];
-            do {
-                const unsigned k = __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned ao = __popc(am & ((1u << k) - 1u));
-                const unsigned bo = B_rowptr[ib + k] + __popc(B_masks[ib + k] & below_c);
-                acc = fma(av[ao], bv[bo], acc);
-            } while (m);
+    for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
+        // pairs of this 32-pair block that touch C row r and C column c
+        unsigned w = hit_t[base + 16 + r] & hit_t[base + c];
+        if (base < ps) w &= 0xFFFFFFFFu << (unsigned)(ps - base);
+        if (base + 32 > pe) w &= 0xFFFFFFFFu >> (unsigned)(base + 32 - pe);
+        while (w) {
+            const int64_t i = base + (__ffs(w) - 1);
+            w &= w - 1;
+            const int2 ab = pairs[i];
+            const unsigned ia = (unsigned)ab.x * 16u, ib = (unsigned)ab.y * 16u;
+            const unsigned am = A_masks[ia + r];
+            unsigned m = am & B_masks_t[ib + c];
+            if (m) {
+                const double* __restrict__ av = A_vals + (A_off[ab.x] + A_rowptr[ia + r]);
+                const double* __restrict__ bv = B_vals + B_off[ab.y];
+                do {
+                    const unsigned k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned ao = __popc(am & ((1u << k) - 1u));
+                    const unsigned bo = B_rowptr[ib + k] + __popc(B_masks[ib + k] & below_c);
+                    acc = fma(av[ao], bv[bo], acc);
+                } while (m);
+            }
         }
     }
     C_vals[n] = acc;
@@ -364,19 +447,42 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     PEM_TRY(pem_alloc(ctx, &C->masks, (size_t)C->tiles * 16));
     PEM_TRY(pem_alloc(ctx, &C->tile_nnz_ptr, (size_t)C->tiles + 1));
     const bool rows_variant = ctx->opt_owner == 1;
-    if (!rows_variant) PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)C->pairs));
-    if (C->tiles > 0 && rows_variant) {
-        k_step2_masks<<<pem_div_up(C->tiles * 16, 256), 256, 0, ctx->stream>>>(
-            C->tiles, C->pair_ptr, C->pair_list, A->masks, B->masks, C->masks, C->tile_nnz_ptr);
+    if (rows_variant) {
+        if (C->tiles > 0) {
+            k_step2_masks<<<pem_div_up(C->tiles * 16, 256), 256, 0, ctx->stream>>>(
+                C->tiles, C->pair_ptr, C->pair_list, A->masks, B->masks, C->masks, C->tile_nnz_ptr);
+            PEM_LAUNCHED();
+        }
+        k_set_last_i64<<<1, 1, 0, ctx->stream>>>(C->tile_nnz_ptr, C->tiles, 0);
         PEM_LAUNCHED();
-    } else if (C->tiles > 0) {
-        k_step2_masks_tile<<<pem_div_up(C->tiles, 128), 128, 0, ctx->stream>>>(
-            C->tiles, C->pair_ptr, C->pair_list, A->masks, B->masks, C->masks, C->tile_nnz_ptr, C->pair_hit);
-        PEM_LAUNCHED();
+        PEM_TRY(pem_scan_exclusive_i64(ctx, C->tile_nnz_ptr, C->tiles + 1));
+    } else {
+        const int64_t nblk = (C->pairs + S2P_THREADS - 1) / S2P_THREADS;
+        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "more than 2^39 tile pairs");
+        PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)nblk * S2P_THREADS));
+        PEM_CK(cudaMemsetAsync(C->masks, 0, (size_t)C->tiles * 32, ctx->stream));
+        if (C->pairs > 0) {
+            int32_t* blk = nullptr;
+            PEM_TRY(pem_alloc(ctx, &blk, (size_t)nblk + 1));
+            k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
+            PEM_LAUNCHED();
+            k_step2_pairs<<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(
+                C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->masks, B->masks,
+                reinterpret_cast<uint32_t*>(C->masks), C->pair_hit);
+            PEM_LAUNCHED();
+            pem_free(ctx, blk);
+        }
+        // per-tile nnz (popcount of the mask) -> exclusive scan, in one pass over the masks
+        auto nnz_it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0),
+                                                      TileNnz{reinterpret_cast<const uint4*>(C->masks), C->tiles});
+        size_t tb = 0;
+        PEM_CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nnz_it, C->tile_nnz_ptr, C->tiles + 1, ctx->stream));
+        char* tmp = nullptr;
+        PEM_TRY(pem_alloc(ctx, &tmp, tb));
+        PEM_CK(cub::DeviceScan::ExclusiveSum(tmp, tb, nnz_it, C->tile_nnz_ptr, C->tiles + 1, ctx->stream));
+        ctx->launches += 2;
+        pem_free(ctx, tmp);
     }
-    k_set_last_i64<<<1, 1, 0, ctx->stream>>>(C->tile_nnz_ptr, C->tiles, 0);
-    PEM_LAUNCHED();
-    PEM_TRY(pem_scan_exclusive_i64(ctx, C->tile_nnz_ptr, C->tiles + 1));
     PEM_CK(cudaMemcpyAsync(ctx->h_scalars, C->tile_nnz_ptr + C->tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     C->nnz = ctx->h_scalars[0];

@@ -50,13 +50,18 @@ typedef enum pem_option {
      *    empty ones (spgemm.cu:271-384 works on the tile structure only; "C tiles" in the
      *    reference's report counts them, spgemm.cu:1420).  C itself is identical either way. */
     PEM_OPT_KEEP_EMPTY_TILES = 1,
-    /* step-1 accumulator choice per tile row: 0 = automatic (default), 1 = force the bitmap
-     * (SPA) path, 2 = force the hash path.  Replaces the reference's global switch
-     * `B_tileCols > 512*32` (spgemm.cu:1142). */
+    /* step-1 algorithm: 0 (default) = automatic: expand-sort-compress over tile products (no
+     * per-row accumulator, no limit on tile columns), except for small operands (<= 64K tiles and a
+     * tile-column window that fits shared memory) where the per-row bitmap path has fewer launches;
+     * 1 = force the per-row windowed bitmap accumulator (the reference's SPA idea,
+     * spgemm.cu:271-384); 2 = force expand-sort-compress.  Replaces the reference's global switch between
+     * SPA and NSPARSE hashing `B_tileCols > 512*32` (spgemm.cu:1142). */
     PEM_OPT_STEP1_PATH = 2,
-    /* thread mapping of steps 2 and 3: 0 (default) = one thread per C' tile / per C nonzero
-     * ("entry-owner", dense lane packing), 1 = sixteen lanes per C' tile, lane = tile row
-     * ("row-owner", accumulators in shared memory).  Results are bit-identical. */
+    /* thread mapping of step 3 (and of step 2 for value 1).  Results are bit-identical.
+     * 0 (default) = automatic (currently always entry-owner: it measured fastest on all workloads)
+     * 1 = row-owner: sixteen lanes per C' tile, lane = tile row (steps 2 and 3)
+     * 2 = entry-owner: one thread per C nonzero (dense lane packing; hypersparse tiles)
+     * 3 = tile-owner: one warp per C' tile, lane = nonzero, pair data shared through shuffles */
     PEM_OPT_OWNER = 3
 } pem_option;
 

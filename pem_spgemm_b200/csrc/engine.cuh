@@ -23,7 +23,7 @@ struct pem_ctx {
     int64_t launches = 0;        // kernels of this library launched on the stream
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
-    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = entry-owner steps 2/3 (default), 1 = row-owner
+    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = auto, 1 = row-owner, 2 = entry-owner, 3 = tile-owner
     int sm_count = 148;
     int smem_optin = 227 * 1024; // max dynamic shared memory per block
     int64_t* h_scalars = nullptr; // pinned, PEM_NSCALARS entries: size read-backs
@@ -113,6 +113,7 @@ struct pem_result {
     int32_t tile_cols = 0;
     int64_t tiles = 0, pairs = 0, nnz = 0, tile_products = 0;
     int stage = 0;                    // 1, 2, 3 = last completed step
+    bool s3_tiles = false;            // step 3 runs a warp per C' tile (dense tiles) instead of a thread per nonzero
     int64_t* row_ptr = nullptr;       // [re-rb+1]
     int32_t* tile_row = nullptr;      // [tiles]
     int32_t* tile_col = nullptr;      // [tiles]

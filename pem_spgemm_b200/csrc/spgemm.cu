@@ -422,6 +422,83 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
     C_vals[n] = acc;
 }
 
+// step 3 (tile-owner): ONE WARP PER C' TILE, lane = C nonzero (32 per pass).  What the entry-owner
+// kernel fetches once per entry and pair - the pair's ids, the A row masks / row pointers, the B row
+// and column masks / row pointers, the two value offsets - is fetched once per WARP and pair here
+// (sixteen lanes load one 16-entry array each, coalesced) and handed to the entry's lane with
+// shuffles; the per-product index arithmetic (rank of k in the A row, rank of c in B row k) also
+// runs on shuffled registers.  Pays off when C tiles are dense (FEM / stencil matrices: ~30
+// nonzeros per tile); same ascending-k fma order as every other variant, so the bits agree.
+constexpr int S3W_THREADS = 256;
+__global__ void __launch_bounds__(S3W_THREADS)
+k_step3_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+              const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
+              const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
+              const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
+              const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
+              const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
+              const uint16_t* __restrict__ B_masks_t, double* __restrict__ C_vals)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, h = lane & 15;
+    const int64_t t = ((int64_t)blockIdx.x * S3W_THREADS + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;                       // whole warps leave together
+    const unsigned cm = Cmasks[t * 16 + h];
+    const int pc = __popc(cm);
+    int incl = pc;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o, 16);
+        if (h >= o) incl += v;
+    }
+    const int crp = incl - pc;                      // first entry of C row h inside the tile
+    const int E = __shfl_sync(FULL, incl, 15);
+    if (E == 0) return;
+    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
+    double* __restrict__ out = C_vals + c_tile_nnz_ptr[t];
+    for (int e0 = 0; e0 < E; e0 += 32) {
+        const int e = e0 + lane;
+        const bool active = e < E;
+        // (r, c) of entry e: r = last row whose first entry is <= e, c = the (e - first)th bit of the row mask
+        int r = 0;
+#pragma unroll
+        for (int step = 8; step > 0; step >>= 1) {
+            const int v = __shfl_sync(FULL, crp, r + step);
+            if (v <= e) r += step;
+        }
+        const unsigned cmr = __shfl_sync(FULL, cm, r);
+        const int first = __shfl_sync(FULL, crp, r);
+        const unsigned c = active ? __fns(cmr, 0, e - first + 1) : 0u;
+        const unsigned below_c = (1u << c) - 1u;
+        double acc = 0.0;
+        int2 ab = pairs[ps];
+        for (int64_t i = ps; i < pe; ++i) {
+            const unsigned ia = (unsigned)ab.x * 16u, ib = (unsigned)ab.y * 16u;
+            const unsigned a_pack = A_masks[ia + h] | ((unsigned)A_rowptr[ia + h] << 16);
+            const unsigned b_pack = B_masks[ib + h] | ((unsigned)B_rowptr[ib + h] << 16);
+            const unsigned bt_h = B_masks_t[ib + h];
+            const double* __restrict__ av = A_vals + A_off[ab.x];
+            const double* __restrict__ bv = B_vals + B_off[ab.y];
+            if (i + 1 < pe) ab = pairs[i + 1];      // next pair's ids while this one is consumed
+            const unsigned ar = __shfl_sync(FULL, a_pack, r);
+            const unsigned am = ar & 0xFFFFu;
+            const unsigned bt = __shfl_sync(FULL, bt_h, c);      // outside the select: every lane must take part
+            unsigned m = active ? (am & bt) : 0u;
+            while (__any_sync(FULL, m != 0)) {
+                const unsigned k = m ? __ffs(m) - 1 : 0u;
+                const unsigned bk = __shfl_sync(FULL, b_pack, k);
+                if (m) {
+                    const unsigned ao = (ar >> 16) + __popc(am & ((1u << k) - 1u));
+                    const unsigned bo = (bk >> 16) + __popc(bk & below_c);   // below_c < 2^16: the row-pointer bits drop out
+                    acc = fma(av[ao], bv[bo], acc);
+                    m &= m - 1;
+                }
+            }
+        }
+        if (active) out[e] = acc;
+    }
+}
+
 __global__ void k_set_last_i64(int64_t* p, int64_t idx, int64_t v) { p[idx] = v; }
 
 }  // namespace
@@ -487,7 +564,11 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     C->nnz = ctx->h_scalars[0];
     C->stage = 2;
-    if (!rows_variant) {          // what the entry-owner step 3 reads: (r,c) per nonzero, first tile per block
+    // step-3 mapping: a thread per nonzero by default; a warp per C' tile on request
+    // (measured on B200, profiles/: the entry-owner kernel wins on every BASELINE config, including the
+    // stencil matrix with ~30 nonzeros per C tile, so the tile-owner kernel is opt-in)
+    C->s3_tiles = ctx->opt_owner == 3;
+    if (!rows_variant && !C->s3_tiles) {   // what the entry-owner step 3 reads: (r,c) per nonzero, first tile per block
         PEM_TRY(pem_result_make_rowcolidx(ctx, C));
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
@@ -505,7 +586,15 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
     if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
-    if (C->nnz > 0 && C->pair_hit) {      // entry-owner variant (step 2 prepared its inputs)
+    if (C->nnz > 0 && C->s3_tiles) {
+        const int64_t nblk = (C->tiles * 32 + S3W_THREADS - 1) / S3W_THREADS;
+        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^34 tiles");
+        k_step3_tiles<<<(unsigned)nblk, S3W_THREADS, 0, ctx->stream>>>(
+            C->tiles, C->pair_ptr, C->pair_list, C->masks, C->tile_nnz_ptr,
+            A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr,
+            B->masks_t, C->vals);
+        PEM_LAUNCHED();
+    } else if (C->nnz > 0 && C->pair_hit) {      // entry-owner variant (step 2 prepared its inputs)
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^39 nonzeros");
         k_step3_entries<<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(

@@ -52,6 +52,25 @@ def test_conversion_matches_tile_oracle(engine, shape, nnz, seed, transpose):
     T.free()
 
 
+def test_dense_blocks_all_step3_variants(engine):
+    """Fully dense 16x16 tiles (256 nonzeros per C tile: eight passes of the tile-owner kernel,
+    a whole block of the entry-owner one) and a ragged dense matrix."""
+    for n in (32, 40):
+        I, J = np.divmod(np.arange(n * n, dtype=np.int32), n)
+        V = np.random.default_rng(n).uniform(-1, 1, n * n)
+        _, _, oC = host.spgemm_from_coo(n, n, I, J, V, False)
+        A = engine.convert_coo(n, n, I, J, V)
+        for owner in (0, 1, 2, 3):
+            engine.set_option(pem.OPT_OWNER, owner)
+            try:
+                C = engine.spgemm(A, A)
+                _assert_same_C(C, oC)
+                C.free()
+            finally:
+                engine.set_option(pem.OPT_OWNER, 0)
+        A.free()
+
+
 def test_conversion_dense_tile_and_empty(engine):
     I, J = np.divmod(np.arange(256, dtype=np.int32), 16)
     V = np.arange(256, dtype=np.float64)
@@ -83,7 +102,7 @@ def test_conversion_input_errors(engine):
     A.free()
 
 
-@pytest.mark.parametrize("step1_path", [0, 1])     # 0: expand-sort-compress (default), 1: windowed bitmap SPA
+@pytest.mark.parametrize("step1_path", [2, 1])     # 2: expand-sort-compress, 1: windowed bitmap SPA (0 = auto picks one of them)
 @pytest.mark.parametrize("keep_empty", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_steps_match_tile_oracle(engine, k, keep_empty, step1_path):
@@ -200,14 +219,16 @@ def test_device_pointer_input_and_pool_reuse(engine):
     A.free()
 
 
-@pytest.mark.parametrize("k", [2, 3, 4])
-def test_row_owner_variant_is_bit_identical(engine, k):
-    """PEM_OPT_OWNER=1 (sixteen lanes per C' tile) must give the same bits as the default."""
+@pytest.mark.parametrize("owner", [1, 2, 3])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_owner_variants_are_bit_identical(engine, k, owner):
+    """PEM_OPT_OWNER = 1 (row-owner), 2 (entry-owner), 3 (tile-owner) must give the same bits as
+    the automatic choice and as the oracle."""
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
     A = engine.convert_coo(rows, cols, I, J, V)
     B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
     C0 = engine.spgemm(A, B)
-    engine.set_option(pem.OPT_OWNER, 1)
+    engine.set_option(pem.OPT_OWNER, owner)
     try:
         C1 = engine.spgemm(A, B)
     finally:
@@ -228,9 +249,10 @@ def test_step1_paths_agree_at_full_size(engine, k):
     name, tb, (rows, cols, I, J, V) = synth.config(k)
     A = engine.convert_coo(rows, cols, I, J, V)
     B = engine.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
-    C0 = engine.spgemm(A, B)
-    engine.set_option(pem.OPT_STEP1_PATH, 1)
+    engine.set_option(pem.OPT_STEP1_PATH, 2)
     try:
+        C0 = engine.spgemm(A, B)
+        engine.set_option(pem.OPT_STEP1_PATH, 1)
         C1 = engine.spgemm(A, B)
     finally:
         engine.set_option(pem.OPT_STEP1_PATH, 0)

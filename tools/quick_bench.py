@@ -13,10 +13,12 @@ ap.add_argument("--keep-empty", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--small", action="store_true")
 ap.add_argument("--owner", type=int, default=0)
+ap.add_argument("--step1", type=int, default=0)
 a = ap.parse_args()
 ctx = pem.Context(0)
 ctx.set_option(pem.OPT_KEEP_EMPTY_TILES, a.keep_empty)
 ctx.set_option(pem.OPT_OWNER, a.owner)
+ctx.set_option(pem.OPT_STEP1_PATH, a.step1)
 for k in a.configs:
     t0 = time.time()
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=a.small)

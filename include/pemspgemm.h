@@ -105,6 +105,10 @@ void* pem_ctx_stream(pem_ctx* ctx);             /* the cudaStream_t all work is 
 int pem_ctx_sync(pem_ctx* ctx);
 /* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
 int64_t pem_ctx_launch_count(const pem_ctx* ctx);
+/* Device time (ms, CUDA events on the context's stream) of the four individually timed kernels of
+ * the last pem_spgemm / pem_spgemm_panel call: [0] k_expand (step 1 product expansion), [1] the
+ * step-1 radix sort, [2] k_step2_pairs, [3] the step-3 numeric kernel.  Returns the count (4). */
+int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n);
 /* Bytes currently reserved by the context's pool (diagnostic). */
 int64_t pem_ctx_pool_bytes(const pem_ctx* ctx);
 

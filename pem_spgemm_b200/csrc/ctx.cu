@@ -92,6 +92,8 @@ int pem_ctx_create(pem_ctx** out, int device)
     if ((e = cudaMalloc((void**)&ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t))) != cudaSuccess) return bail(e);
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
+    for (auto& ev : ctx->kev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     size_t free_b = 0, total_b = 0;
@@ -109,6 +111,8 @@ void pem_ctx_destroy(pem_ctx* ctx)
     for (auto& kv : ctx->live_blocks) cudaFreeAsync(kv.first, ctx->stream);   // handles the caller leaked
     cudaStreamSynchronize(ctx->stream);
     for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->kev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -146,6 +150,13 @@ int pem_ctx_sync(pem_ctx* ctx)
 }
 
 int64_t pem_ctx_launch_count(const pem_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n)
+{
+    if (!ctx || !ms || n < KT_N) return PEM_ERR_ARG;
+    for (int i = 0; i < KT_N; ++i) ms[i] = ctx->kt_ms[i];
+    return KT_N;
+}
 
 int64_t pem_ctx_pool_bytes(const pem_ctx* ctx)
 {

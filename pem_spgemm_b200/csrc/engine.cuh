@@ -14,6 +14,8 @@
 // context
 // ---------------------------------------------------------------------------------------
 enum { PEM_NSCALARS = 24, PEM_NEVENTS = 8 };
+// kernels timed individually (CUDA events on the context's stream) for the roofline report
+enum { KT_EXPAND = 0, KT_SORT = 1, KT_PAIRS = 2, KT_NUMERIC = 3, KT_N = 4 };
 
 struct pem_ctx {
     int device = 0;
@@ -29,6 +31,9 @@ struct pem_ctx {
     int64_t* h_scalars = nullptr; // pinned, PEM_NSCALARS entries: size read-backs
     int64_t* d_scalars = nullptr; // device mirror the kernels reduce into
     cudaEvent_t ev[PEM_NEVENTS] = {};
+    cudaEvent_t kev[2 * KT_N] = {};   // begin/end pairs of the individually timed kernels
+    bool kt_seen[KT_N] = {};
+    double kt_ms[KT_N] = {};          // resolved by pem_spgemm_panel after its final sync
     // caching layer over the pool: freed blocks are kept by size and handed out again in stream
     // order (all work of a context is on one stream), so a repeated SpGEMM allocates nothing
     std::multimap<size_t, void*> free_blocks;
@@ -59,6 +64,9 @@ struct pem_ctx {
         cudaError_t e__ = cudaGetLastError();                                            \
         if (e__ != cudaSuccess) return ctx->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
     } while (0)
+
+#define KT_BEGIN(id) do { cudaEventRecord(ctx->kev[2 * (id)], ctx->stream); } while (0)
+#define KT_END(id) do { cudaEventRecord(ctx->kev[2 * (id) + 1], ctx->stream); ctx->kt_seen[id] = true; } while (0)
 
 #define PEM_TRY(expr)                    \
     do {                                 \

@@ -543,9 +543,11 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
             PEM_TRY(pem_alloc(ctx, &blk, (size_t)nblk + 1));
             k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
             PEM_LAUNCHED();
+            KT_BEGIN(KT_PAIRS);
             k_step2_pairs<<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(
                 C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->masks, B->masks,
                 reinterpret_cast<uint32_t*>(C->masks), C->pair_hit);
+            KT_END(KT_PAIRS);
             PEM_LAUNCHED();
             pem_free(ctx, blk);
         }
@@ -586,6 +588,7 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
     if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
+    KT_BEGIN(KT_NUMERIC);
     if (C->nnz > 0 && C->s3_tiles) {
         const int64_t nblk = (C->tiles * 32 + S3W_THREADS - 1) / S3W_THREADS;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^34 tiles");
@@ -610,6 +613,7 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
             A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr, C->vals);
         PEM_LAUNCHED();
     }
+    KT_END(KT_NUMERIC);
     C->stage = 3;
     return PEM_OK;
 }
@@ -639,6 +643,7 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     auto w0 = std::chrono::high_resolution_clock::now();
     pem_result* C = nullptr;
+    for (int i = 0; i < KT_N; ++i) { ctx->kt_seen[i] = false; ctx->kt_ms[i] = 0.0; }
     PEM_CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     PEM_TRY(pem_step1_symbolic(ctx, A, B, rb, re, &C));
     cudaEventRecord(ctx->ev[3], ctx->stream);
@@ -650,6 +655,11 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
         rc = ctx->fail_cuda(cudaGetLastError(), "cudaStreamSynchronize after step 3", __FILE__, __LINE__);
     if (rc != PEM_OK) { pem_result_free(ctx, C); return rc; }
     auto w1 = std::chrono::high_resolution_clock::now();
+    for (int i = 0; i < KT_N; ++i) {
+        float ms = 0.f;
+        if (ctx->kt_seen[i] && cudaEventElapsedTime(&ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]) == cudaSuccess) ctx->kt_ms[i] = ms;
+        else (void)cudaGetLastError();
+    }
     if (times) {
         float s1 = 0, s2 = 0, s3 = 0;
         cudaEventElapsedTime(&s1, ctx->ev[2], ctx->ev[3]);

@@ -298,9 +298,11 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     if (staged) {
         E_TRY(pem_alloc(ctx, &key_b, (size_t)P));
         E_TRY(pem_alloc(ctx, &val_b, (size_t)P));
+        KT_BEGIN(KT_EXPAND);
         k_expand<KeyT, 1><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
             np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
             ctx->opt_keep_empty, nullptr, chunk_off, key_b, val_b);
+        KT_END(KT_EXPAND);
         E_LAUNCHED();
     } else {
         k_expand<KeyT, 0><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
@@ -340,7 +342,9 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         size_t tb = 0;
         E_CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, F, 0, wbits + rbits, ctx->stream));
         E_TRY(pem_alloc(ctx, &tmp, tb));
+        KT_BEGIN(KT_SORT);
         E_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, F, 0, wbits + rbits, ctx->stream));
+        KT_END(KT_SORT);
         ctx->launches += 2 + (wbits + rbits + 7) / 8;
         pem_free(ctx, tmp);
         if (dk.Current() != key_a) { std::swap(key_a, key_b); std::swap(val_a, val_b); }

@@ -187,6 +187,49 @@ k_tile_flop(const uint16_t* __restrict__ masks_t, const int32_t* __restrict__ ti
     if (f) atomicAdd(&tile_row_flop[tile_row[t]], f);
 }
 
+// ---- row slices (see pem_tiled::srow_ptr) ------------------------------------------------------
+// count: thread per tile, one atomic per occupied row of the tile
+__global__ void __launch_bounds__(256)
+k_srow_count(const uint16_t* __restrict__ row_occ, const int32_t* __restrict__ tile_row, int cnt,
+             unsigned long long* __restrict__ srow_cnt)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    unsigned occ = row_occ[t];
+    const size_t base = (size_t)tile_row[t] * 16;
+    while (occ) {
+        const int r = __ffs(occ) - 1;
+        occ &= occ - 1;
+        atomicAdd(&srow_cnt[base + r], 1ull);
+    }
+}
+
+// fill: warp per tile row; the row's tiles are visited 32 at a time in tile-column order and every
+// occupied (tile, row) places the tile id at ballot rank, so each slice keeps tile-column order
+__global__ void __launch_bounds__(256)
+k_srow_fill(int tile_rows, const int32_t* __restrict__ tile_row_ptr, const uint16_t* __restrict__ row_occ,
+            const int64_t* __restrict__ srow_ptr, int32_t* __restrict__ srow_tile)
+{
+    const int tr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tr >= tile_rows) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int ts = tile_row_ptr[tr], te = tile_row_ptr[tr + 1];
+    int64_t at[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) at[r] = srow_ptr[(size_t)tr * 16 + r];
+    for (int q0 = ts; q0 < te; q0 += 32) {
+        const int q = q0 + lane;
+        const unsigned occ = q < te ? (unsigned)row_occ[q] : 0u;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (occ >> r) & 1u);
+            if ((occ >> r) & 1u) srow_tile[at[r] + __popc(bal & lt)] = q;
+            at[r] += __popc(bal);
+        }
+    }
+}
+
 bool is_device_ptr(const void* p)
 {
     cudaPointerAttributes at;
@@ -344,6 +387,42 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     *out = T;
     return PEM_OK;
 }
+
+}  // extern "C"
+
+// Row slices of a tiled matrix, built once and cached on the handle (the handle is logically
+// const for the caller; the cache is the one mutable part).
+int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* Bc)
+{
+    pem_tiled* B = const_cast<pem_tiled*>(Bc);
+    if (B->srow_ptr) return PEM_OK;
+    const size_t rows16 = (size_t)B->tile_rows * 16;
+    int64_t* ptr = nullptr;
+    PEM_TRY(pem_alloc(ctx, &ptr, rows16 + 1));
+    PEM_CK(cudaMemsetAsync(ptr, 0, (rows16 + 1) * 8, ctx->stream));
+    if (B->tiles) {
+        k_srow_count<<<pem_div_up(B->tiles, 256), 256, 0, ctx->stream>>>(B->row_occ, B->tile_row_idx, B->tiles,
+                                                                         (unsigned long long*)ptr);
+        PEM_LAUNCHED();
+    }
+    PEM_TRY(pem_scan_exclusive_i64(ctx, ptr, (int64_t)rows16 + 1));
+    PEM_CK(cudaMemcpyAsync(ctx->h_scalars, ptr + rows16, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PEM_CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t total = ctx->h_scalars[0];
+    int32_t* tl = nullptr;
+    PEM_TRY(pem_alloc(ctx, &tl, (size_t)total));
+    if (B->tiles) {
+        k_srow_fill<<<pem_div_up((int64_t)B->tile_rows * 32, 256), 256, 0, ctx->stream>>>(
+            B->tile_rows, B->tile_row_ptr, B->row_occ, ptr, tl);
+        PEM_LAUNCHED();
+    }
+    B->srow_ptr = ptr;
+    B->srow_total = total;
+    B->srow_tile = tl;
+    return PEM_OK;
+}
+
+extern "C" {
 
 int pem_count_flop(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, uint64_t* flop)
 {

@@ -129,7 +129,7 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
     switch (option) {
         case PEM_OPT_KEEP_EMPTY_TILES: ctx->opt_keep_empty = value != 0; return PEM_OK;
         case PEM_OPT_STEP1_PATH:
-            if (value < 0 || value > 2) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP1_PATH must be 0, 1 or 2");
+            if (value < 0 || value > 4) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP1_PATH must be 0..4");
             ctx->opt_step1_path = (int)value;
             return PEM_OK;
         case PEM_OPT_OWNER:
@@ -219,7 +219,7 @@ void pem_tiled_free(pem_ctx* ctx, pem_tiled* t)
     pem_free(ctx, t->vals); pem_free(ctx, t->tile_nnz_ptr); pem_free(ctx, t->masks);
     pem_free(ctx, t->masks_t); pem_free(ctx, t->row_ptr); pem_free(ctx, t->tile_row_ptr);
     pem_free(ctx, t->tile_col_idx); pem_free(ctx, t->tile_row_idx); pem_free(ctx, t->col_occ);
-    pem_free(ctx, t->row_occ);
+    pem_free(ctx, t->row_occ); pem_free(ctx, t->srow_ptr); pem_free(ctx, t->srow_tile);
     delete t;
 }
 

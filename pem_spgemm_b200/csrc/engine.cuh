@@ -110,6 +110,11 @@ struct pem_tiled {
     int32_t* tile_row_idx = nullptr;  // [tiles]
     uint16_t* col_occ = nullptr;      // [tiles]
     uint16_t* row_occ = nullptr;      // [tiles]
+    // row slices, built on first use as a B operand of step 1 (pem_tiled_build_srow): for every
+    // matrix row s the ids of the tiles that hold a nonzero of row s, in tile-column order
+    int64_t* srow_ptr = nullptr;      // [rows16+1], rows16 = 16*tile_rows
+    int32_t* srow_tile = nullptr;     // [srow_ptr[rows16]]
+    int64_t srow_total = 0;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -154,3 +159,4 @@ enum {
 int pem_scan_exclusive_i64(pem_ctx* ctx, int64_t* d_inout, int64_t n);  // in place, n elements
 extern "C" int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C);
 int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C);  // step1_esc.cu
+int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* B);                              // convert.cu

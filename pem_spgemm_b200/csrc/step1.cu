@@ -513,7 +513,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     // small operands are launch-bound: the per-row bitmap path below needs ~8 launches and 2 host
     // syncs, expand-sort-compress ~20 and 3
     const bool small = (int64_t)A->tiles + B->tiles <= 65536 && B->tile_cols <= 65536;
-    if (ctx->opt_step1_path == 2 || (ctx->opt_step1_path == 0 && !small)) {     // expand-sort-compress (step1_esc.cu)
+    if (ctx->opt_step1_path >= 2 || (ctx->opt_step1_path == 0 && !small)) {     // expand-sort-compress (step1_esc.cu)
         int rc = pem_alloc(ctx, &C->row_ptr, (size_t)nrows + 1);
         if (rc == PEM_OK) rc = pem_step1_esc(ctx, A, B, C);
         if (rc != PEM_OK) { pem_result_free(ctx, C); return rc; }

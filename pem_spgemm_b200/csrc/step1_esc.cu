@@ -51,23 +51,80 @@ constexpr int EX_WARPS = EX_THREADS / 32;
 // thread per A tile of the panel
 __global__ void __launch_bounds__(256)
 k_tile_products(int p0, int np, int rb, const int32_t* __restrict__ Acol, const int32_t* __restrict__ Arow,
+                const uint16_t* __restrict__ AcolOcc,
                 const int32_t* __restrict__ Brp, const int32_t* __restrict__ Bcol,
-                int64_t* __restrict__ plen, int32_t* __restrict__ bfirst, int* __restrict__ jmin,
-                int* __restrict__ jmax)
+                const int64_t* __restrict__ srow_ptr,
+                int64_t* __restrict__ plen, int32_t* __restrict__ bfirst, int64_t* __restrict__ icnt,
+                int* __restrict__ jmin, int* __restrict__ jmax, int64_t* __restrict__ scalars)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > np) return;
-    if (i == np) { plen[i] = 0; return; }
+    unsigned long long cost = 0, items = 0;
+    if (i < np) {
+        const int p = p0 + i;
+        const int k = Acol[p];
+        const int bs = Brp[k], be = Brp[k + 1];
+        plen[i] = be - bs;
+        bfirst[i] = bs;
+        if (be > bs) {
+            const int row = Arow[p] - rb;
+            const int lo = Bcol[bs], hi = Bcol[be - 1];
+            if (lo < jmin[row]) atomicMin(&jmin[row], lo);
+            if (hi > jmax[row]) atomicMax(&jmax[row], hi);
+        }
+        if (srow_ptr) {            // cost of expanding this tile through B's row slices instead
+            unsigned occ = AcolOcc[p];
+            items = __popc(occ);
+            icnt[i] = (int64_t)items;
+            const int64_t* sp = srow_ptr + (size_t)k * 16;
+            while (occ) {
+                const int c = __ffs(occ) - 1;
+                occ &= occ - 1;
+                cost += (unsigned long long)(sp[c + 1] - sp[c]);
+            }
+        }
+    } else if (i == np) {
+        plen[i] = 0;
+        if (srow_ptr) icnt[i] = 0;
+    }
+    if (srow_ptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cost += __shfl_xor_sync(0xffffffffu, cost, o);
+            items += __shfl_xor_sync(0xffffffffu, items, o);
+        }
+        if ((threadIdx.x & 31) == 0 && items) {
+            atomicAdd((unsigned long long*)&scalars[SC_T2], cost);
+            atomicAdd((unsigned long long*)&scalars[SC_T1], items);
+        }
+    }
+}
+
+// row-sliced expansion: one work item per (A tile p, occupied tile column c of p); its products are
+// the tiles of B's row slice 16*k + c.  A B tile reachable through several columns of p is kept
+// only for the lowest common one: item_mask = colOcc(p) below c, kept iff rowOcc(q) & item_mask == 0.
+__global__ void __launch_bounds__(256)
+k_items(int p0, int np, const int32_t* __restrict__ Acol, const uint16_t* __restrict__ AcolOcc,
+        const int64_t* __restrict__ srow_ptr, const int64_t* __restrict__ ioff, int64_t n_items,
+        int64_t* __restrict__ plen, int32_t* __restrict__ bfirst, int32_t* __restrict__ item_p,
+        uint16_t* __restrict__ item_mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) plen[n_items] = 0;
+    if (i >= np) return;
     const int p = p0 + i;
-    const int k = Acol[p];
-    const int bs = Brp[k], be = Brp[k + 1];
-    plen[i] = be - bs;
-    bfirst[i] = bs;
-    if (be > bs) {
-        const int row = Arow[p] - rb;
-        const int lo = Bcol[bs], hi = Bcol[be - 1];
-        if (lo < jmin[row]) atomicMin(&jmin[row], lo);
-        if (hi > jmax[row]) atomicMax(&jmax[row], hi);
+    unsigned occ = AcolOcc[p];
+    const unsigned all = occ;
+    const int64_t* sp = srow_ptr + (size_t)Acol[p] * 16;
+    int64_t it = ioff[i];
+    while (occ) {
+        const int c = __ffs(occ) - 1;
+        occ &= occ - 1;
+        const int64_t first = sp[c];
+        plen[it] = sp[c + 1] - first;
+        bfirst[it] = (int32_t)(uint32_t)first;
+        item_p[it] = p;
+        item_mask[it] = (uint16_t)(all & ((1u << c) - 1u));
+        ++it;
     }
 }
 
@@ -103,10 +160,13 @@ k_merge_split(int nchunks, int np, int64_t P, const int64_t* __restrict__ pptr, 
 
 // MODE 0: count kept products per chunk.  MODE 1: also write them (at out_base[b], or at the chunk's
 // first product index when out_base is null).
-template <class KeyT, int MODE>
+// SLICED: the work items are (A tile, column) pairs over B's row slices (k_items) instead of A tiles
+// over B' rows; item_p / srow_tile translate item -> A tile and slice position -> B tile.
+template <class KeyT, int MODE, bool SLICED>
 __global__ void __launch_bounds__(EX_THREADS)
 k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, const int32_t* __restrict__ split,
-         const int32_t* __restrict__ bfirst, const uint16_t* __restrict__ AcolOcc,
+         const int32_t* __restrict__ bfirst, const uint16_t* __restrict__ item_mask,
+         const int32_t* __restrict__ item_p, const int32_t* __restrict__ srow_tile,
          const int32_t* __restrict__ Arow, const int32_t* __restrict__ Bcol,
          const uint16_t* __restrict__ BrowOcc, const int* __restrict__ jmin, int wbits, int keep_empty,
          const int64_t* __restrict__ out_base, int64_t* __restrict__ chunk_cnt,
@@ -129,7 +189,7 @@ k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, co
         s_rel[t] = r;
         if (t < nt) {
             s_q0[t] = (unsigned)bfirst[i0 + t] - (unsigned)r;
-            s_occ[t] = keep_empty ? (unsigned short)0xFFFFu : AcolOcc[p0 + i0 + t];
+            s_occ[t] = (!SLICED && keep_empty) ? (unsigned short)0xFFFFu : item_mask[i0 + t];
         }
     }
     __syncthreads();
@@ -160,13 +220,21 @@ k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, co
             qq[u] = (int)(s_q0[t] + (unsigned)g);
         }
     }
+    if (SLICED) {
+#pragma unroll
+        for (int u = 0; u < EX_ITEMS; ++u)
+            if (qq[u] >= 0) qq[u] = srow_tile[(unsigned)qq[u]];
+    }
     unsigned occ[EX_ITEMS];
 #pragma unroll
-    for (int u = 0; u < EX_ITEMS; ++u) occ[u] = qq[u] >= 0 ? (unsigned)BrowOcc[qq[u]] : 0u;
+    for (int u = 0; u < EX_ITEMS; ++u) {
+        occ[u] = 0u;
+        if (qq[u] >= 0 && (!SLICED || s_occ[tq[u]] != 0)) occ[u] = (unsigned)BrowOcc[qq[u]];
+    }
     unsigned keepbits = 0, mine = 0;
 #pragma unroll
     for (int u = 0; u < EX_ITEMS; ++u) {
-        const bool keep = qq[u] >= 0 && (occ[u] & s_occ[tq[u]]) != 0;
+        const bool keep = qq[u] >= 0 && (SLICED ? (occ[u] & s_occ[tq[u]]) == 0 : (occ[u] & s_occ[tq[u]]) != 0);
         keepbits |= (unsigned)keep << u;
         mine += keep;
     }
@@ -192,7 +260,7 @@ k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, co
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int64_t at = pos + __popc(bal & lt);
-            const int p = p0 + i0 + tq[u];
+            const int p = SLICED ? item_p[i0 + tq[u]] : p0 + i0 + tq[u];
             const int row = Arow[p] - rb;
             const int j = Bcol[qq[u]];
             out_key[at] = ((KeyT)(unsigned)row << wbits) | (KeyT)(unsigned)(j - jmin[row]);
@@ -261,9 +329,12 @@ inline int h_bits(int64_t n)
     return b;
 }
 
-template <class KeyT>
+// np work items with product prefix pptr and first-product index bfirst; item_p/srow_tile are null
+// for the tile-level expansion (item i = A tile p0 + i) and set for the row-sliced one
+template <class KeyT, bool SLICED>
 int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C, int p0, int np, int64_t P,
-            int wbits, int rbits, const int64_t* pptr, const int32_t* bfirst, const int* jmin)
+            int wbits, int rbits, const int64_t* pptr, const int32_t* bfirst, const uint16_t* item_mask,
+            const int32_t* item_p, const int* jmin)
 {
     const int nrows = C->re - C->rb, rb = C->rb;
     const int64_t total = (int64_t)np + P;
@@ -299,15 +370,15 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         E_TRY(pem_alloc(ctx, &key_b, (size_t)P));
         E_TRY(pem_alloc(ctx, &val_b, (size_t)P));
         KT_BEGIN(KT_EXPAND);
-        k_expand<KeyT, 1><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
-            np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
-            ctx->opt_keep_empty, nullptr, chunk_off, key_b, val_b);
+        k_expand<KeyT, 1, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+            np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
+            B->row_occ, jmin, wbits, ctx->opt_keep_empty, nullptr, chunk_off, key_b, val_b);
         KT_END(KT_EXPAND);
         E_LAUNCHED();
     } else {
-        k_expand<KeyT, 0><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
-            np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
-            ctx->opt_keep_empty, nullptr, chunk_off, nullptr, nullptr);
+        k_expand<KeyT, 0, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+            np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
+            B->row_occ, jmin, wbits, ctx->opt_keep_empty, nullptr, chunk_off, nullptr, nullptr);
         E_LAUNCHED();
     }
     E_CK(cudaMemsetAsync(chunk_off + nchunks, 0, 8, ctx->stream));
@@ -328,9 +399,9 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         pem_free(ctx, key_b);
         pem_free(ctx, val_b);
     } else {
-        k_expand<KeyT, 1><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
-            np, p0, rb, P, pptr, split, bfirst, A->col_occ, A->tile_row_idx, B->tile_col_idx, B->row_occ, jmin, wbits,
-            ctx->opt_keep_empty, chunk_off, nullptr, key_a, val_a);
+        k_expand<KeyT, 1, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+            np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
+            B->row_occ, jmin, wbits, ctx->opt_keep_empty, chunk_off, nullptr, key_a, val_a);
         E_LAUNCHED();
     }
     // stable radix sort by (row, column) over the bits in use
@@ -407,14 +478,25 @@ int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_resu
     }
     const int np = p1 - p0;
     if (np == 0) return PEM_OK;
-    int64_t* pptr = nullptr;
-    int32_t* bfirst = nullptr;
+    int64_t *pptr = nullptr, *icnt = nullptr, *pptr_s = nullptr;
+    int32_t *bfirst = nullptr, *bfirst_s = nullptr, *item_p = nullptr;
+    uint16_t* item_mask = nullptr;
     int *jmin = nullptr, *jmax = nullptr;
-    auto cleanup = [&]() { pem_free(ctx, pptr); pem_free(ctx, bfirst); pem_free(ctx, jmin); pem_free(ctx, jmax); };
+    auto cleanup = [&]() {
+        pem_free(ctx, pptr); pem_free(ctx, bfirst); pem_free(ctx, jmin); pem_free(ctx, jmax); pem_free(ctx, icnt);
+        pem_free(ctx, pptr_s); pem_free(ctx, bfirst_s); pem_free(ctx, item_p); pem_free(ctx, item_mask);
+    };
 #define E_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) { cleanup(); return rc_; } } while (0)
 #define E_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return ctx->fail_cuda(e_, #call, __FILE__, __LINE__); } } while (0)
+    // PEM_OPT_STEP1_PATH: 3 forces the tile-level expansion, 4 the row-sliced one; otherwise the
+    // cheaper of the two (product counts are known before anything is expanded).  Reference-faithful
+    // empty tiles exist only at tile level.
+    const bool consider_sliced = !ctx->opt_keep_empty && ctx->opt_step1_path != 3;
+    if (consider_sliced) E_TRY(pem_tiled_build_srow(ctx, B));
+    const int64_t* srow_ptr = consider_sliced ? B->srow_ptr : nullptr;
     E_TRY(pem_alloc(ctx, &pptr, (size_t)np + 1));
     E_TRY(pem_alloc(ctx, &bfirst, (size_t)np));
+    if (consider_sliced) E_TRY(pem_alloc(ctx, &icnt, (size_t)np + 1));
     E_TRY(pem_alloc(ctx, &jmin, (size_t)nrows));
     E_TRY(pem_alloc(ctx, &jmax, (size_t)nrows));
     E_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
@@ -422,7 +504,8 @@ int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_resu
     ++ctx->launches;
     E_CK(cudaMemsetAsync(jmax, 0xFF, (size_t)nrows * 4, ctx->stream));   // -1
     k_tile_products<<<pem_div_up((int64_t)np + 1, 256), 256, 0, ctx->stream>>>(
-        p0, np, rb, A->tile_col_idx, A->tile_row_idx, B->tile_row_ptr, B->tile_col_idx, pptr, bfirst, jmin, jmax);
+        p0, np, rb, A->tile_col_idx, A->tile_row_idx, A->col_occ, B->tile_row_ptr, B->tile_col_idx, srow_ptr,
+        pptr, bfirst, icnt, jmin, jmax, ctx->d_scalars);
     ++ctx->launches;
     E_CK(cudaGetLastError());
     E_TRY(pem_scan_exclusive_i64(ctx, pptr, (int64_t)np + 1));
@@ -431,16 +514,36 @@ int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_resu
     E_CK(cudaGetLastError());
     E_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     E_CK(cudaStreamSynchronize(ctx->stream));
-    const int64_t P = ctx->h_scalars[SC_SUMP];
+    const int64_t P_tile = ctx->h_scalars[SC_SUMP];
+    const int64_t P_sliced = ctx->h_scalars[SC_T2], n_items = ctx->h_scalars[SC_T1];
     const int64_t maxw = ctx->h_scalars[SC_MAXWIN];
-    C->tile_products = P;
+    C->tile_products = P_tile;
     int rc = PEM_OK;
-    if (P > 0) {
+    if (P_tile > 0) {
         const int wbits = h_bits(maxw), rbits = h_bits(nrows);
-        if (wbits + rbits <= 32)
-            rc = esc_run<uint32_t>(ctx, A, B, C, p0, np, P, wbits, rbits, pptr, bfirst, jmin);
+        // the sliced expansion pays an extra indirection per product: take it when it at least halves the products
+        const bool sliced = consider_sliced && n_items > 0 && n_items < 0x7fffffffLL && B->srow_total < 0x7fffffffLL &&
+                            (ctx->opt_step1_path == 4 || 2 * P_sliced < P_tile);
+        if (sliced) {
+            C->tile_products = P_sliced;
+            E_TRY(pem_scan_exclusive_i64(ctx, icnt, (int64_t)np + 1));
+            E_TRY(pem_alloc(ctx, &pptr_s, (size_t)n_items + 1));
+            E_TRY(pem_alloc(ctx, &bfirst_s, (size_t)n_items));
+            E_TRY(pem_alloc(ctx, &item_p, (size_t)n_items));
+            E_TRY(pem_alloc(ctx, &item_mask, (size_t)n_items));
+            k_items<<<pem_div_up(np, 256), 256, 0, ctx->stream>>>(p0, np, A->tile_col_idx, A->col_occ, srow_ptr, icnt, n_items,
+                                                                  pptr_s, bfirst_s, item_p, item_mask);
+            ++ctx->launches;
+            E_CK(cudaGetLastError());
+            E_TRY(pem_scan_exclusive_i64(ctx, pptr_s, n_items + 1));
+            if (wbits + rbits <= 32)
+                rc = esc_run<uint32_t, true>(ctx, A, B, C, p0, (int)n_items, P_sliced, wbits, rbits, pptr_s, bfirst_s, item_mask, item_p, jmin);
+            else
+                rc = esc_run<uint64_t, true>(ctx, A, B, C, p0, (int)n_items, P_sliced, wbits, rbits, pptr_s, bfirst_s, item_mask, item_p, jmin);
+        } else if (wbits + rbits <= 32)
+            rc = esc_run<uint32_t, false>(ctx, A, B, C, p0, np, P_tile, wbits, rbits, pptr, bfirst, A->col_occ + p0, nullptr, jmin);
         else
-            rc = esc_run<uint64_t>(ctx, A, B, C, p0, np, P, wbits, rbits, pptr, bfirst, jmin);
+            rc = esc_run<uint64_t, false>(ctx, A, B, C, p0, np, P_tile, wbits, rbits, pptr, bfirst, A->col_occ + p0, nullptr, jmin);
     }
 #undef E_TRY
 #undef E_CK

@@ -102,7 +102,8 @@ def test_conversion_input_errors(engine):
     A.free()
 
 
-@pytest.mark.parametrize("step1_path", [2, 1])     # 2: expand-sort-compress, 1: windowed bitmap SPA (0 = auto picks one of them)
+# 3: expand-sort-compress at tile level, 4: ... through B's row slices, 1: windowed bitmap SPA (0/2 pick one of them)
+@pytest.mark.parametrize("step1_path", [3, 4, 1])
 @pytest.mark.parametrize("keep_empty", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_steps_match_tile_oracle(engine, k, keep_empty, step1_path):
@@ -242,14 +243,15 @@ def test_owner_variants_are_bit_identical(engine, k, owner):
     C0.free(); C1.free(); A.free(); B.free()
 
 
+@pytest.mark.parametrize("esc", [3, 4])
 @pytest.mark.parametrize("k", [2, 3])
-def test_step1_paths_agree_at_full_size(engine, k):
+def test_step1_paths_agree_at_full_size(engine, k, esc):
     """BASELINE.json sizes (too big for the numpy tile oracle): the two step-1 algorithms must
     produce identical C' structure and pair lists, and step 3 identical value bits."""
     name, tb, (rows, cols, I, J, V) = synth.config(k)
     A = engine.convert_coo(rows, cols, I, J, V)
     B = engine.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
-    engine.set_option(pem.OPT_STEP1_PATH, 2)
+    engine.set_option(pem.OPT_STEP1_PATH, esc)
     try:
         C0 = engine.spgemm(A, B)
         engine.set_option(pem.OPT_STEP1_PATH, 1)

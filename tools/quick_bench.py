@@ -12,6 +12,7 @@ ap.add_argument("--check", action="store_true")
 ap.add_argument("--keep-empty", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--small", action="store_true")
+ap.add_argument("--panels", type=int, default=1, help="multiply in this many sequential tile-row panels (results freed panel by panel)")
 ap.add_argument("--owner", type=int, default=0)
 ap.add_argument("--step1", type=int, default=0)
 a = ap.parse_args()
@@ -28,14 +29,28 @@ for k in a.configs:
     B = ctx.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
     flop = ctx.count_flop(A, B)
     best = None
+    bounds = ctx.partition_panels(A, B, a.panels)
     for r in range(a.reps):
         t = pem.Times()
-        C = ctx.spgemm(A, B, times=t)
-        info = C.info
+        tot = dict(tiles=0, pairs=0, nnz=0, tile_products=0)
+        for pn in range(a.panels):
+            tp = pem.Times()
+            C = ctx.spgemm(A, B, times=tp, panel=(int(bounds[pn]), int(bounds[pn + 1])) if a.panels > 1 else None)
+            for f in ("step1_ms", "step2_ms", "step3_ms", "total_ms"):
+                setattr(t, f, getattr(t, f) + getattr(tp, f))
+            i = C.info
+            for f in tot:
+                tot[f] += getattr(i, f)
+            if pn + 1 < a.panels:
+                C.free()
+        class info: pass
+        for f in tot:
+            setattr(info, f, tot[f])
         if best is None or t.total_ms < best.total_ms:
             best = t
         if os.environ.get('PEM_QB_VERBOSE'):
-            print(f'   rep {r}: step1 {t.step1_ms:.3f} step2 {t.step2_ms:.3f} step3 {t.step3_ms:.3f} total {t.total_ms:.3f} pool {ctx.pool_bytes/2**30:.2f} GiB', flush=True)
+            print(f'   rep {r}: step1 {t.step1_ms:.3f} step2 {t.step2_ms:.3f} step3 {t.step3_ms:.3f} total {t.total_ms:.3f} pool {ctx.pool_bytes/2**30:.2f} GiB'
+                  f' | last panel kernels {" ".join(f"{k}={v:.3f}" for k, v in ctx.kernel_ms().items())}', flush=True)
         if r + 1 < a.reps:
             C.free()
     print(f"{name}: gen {tg:.1f}s nnzA {A.info.nnz} tilesA {A.info.tiles} flop {flop} | convert {tc.convert_total_ms:.2f} ms "

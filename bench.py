@@ -50,14 +50,34 @@ def algorithmic_bytes(a_rows, a_nnz, b_rows, b_nnz, c_rows, c_nnz):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML from a thread of this
+    process (cheap: no extra process hammering the driver), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.nvml, self.stop_flag = device, [], None, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.device)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -67,19 +87,38 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    why = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append([str(sm), str(self.mx)] + ["Active" if why & bit else "Not Active"
+                                                            for bit in (0x8, 0x40, 0x20, 0x4)])
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -90,7 +129,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def load_workload(k):
@@ -178,6 +217,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--keep-empty", type=int, default=0)
+    ap.add_argument("--subpanels", type=int, default=0,
+                    help="sequential tile-row panels per rank (0 = auto: config 5's C does not fit one GPU in tiled form "
+                         "unless it is produced and consumed panel by panel)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -207,8 +249,9 @@ def main():
     A = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
     B = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A
     flop = ctx.count_flop(A, B)
-    bounds = ctx.partition_panels(A, B, world)
-    panel = (int(bounds[rank]), int(bounds[rank + 1]))
+    sub = args.subpanels or (max(1, -(-8 // world)) if args.config == 5 else 1)
+    bounds = ctx.partition_panels(A, B, world * sub)
+    panels = [(int(bounds[rank * sub + i]), int(bounds[rank * sub + i + 1])) for i in range(sub)]
 
     def barrier():
         ctx.sync()
@@ -216,12 +259,22 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def one_step(times=None):
-        C = ctx.spgemm(A, B, times=times, panel=panel)
-        info = C.info
+    def one_step(times=None, kern=None):
+        nnz = tiles = pairs = 0
+        for pn in panels:               # this rank's panels, one after the other (results freed in between)
+            tp = pem.Times()
+            C = ctx.spgemm(A, B, times=tp, panel=pn)
+            info = C.info
+            nnz += info.nnz; tiles += info.tiles; pairs += info.pairs
+            C.free()
+            if times is not None:
+                for f in ("step1_ms", "step2_ms", "step3_ms"):
+                    setattr(times, f, getattr(times, f) + getattr(tp, f))
+            if kern is not None:
+                for k, v in ctx.kernel_ms().items():
+                    kern[k] = kern.get(k, 0.0) + v
         # the path's only exchange: per-shard sizes -> global offsets of every shard of C
-        layout = pdist.exchange_shard_sizes(info.nnz, info.tiles, info.pairs, device="cuda")
-        C.free()
+        layout = pdist.exchange_shard_sizes(nnz, tiles, pairs, device="cuda")
         return layout.totals
 
     for _ in range(args.warmup):
@@ -237,7 +290,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t = pem.Times()
         e0.record(stream)
-        sizes = one_step(t)
+        kd = {}
+        sizes = one_step(t, kd)
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -245,7 +299,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         step_ms.append(float(ms.item()))
         s1.append(t.step1_ms); s2.append(t.step2_ms); s3.append(t.step3_ms)
-        kms.append(ctx.kernel_ms())
+        kms.append(kd)
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     c_nnz, c_tiles, c_pairs = (int(x) for x in sizes.tolist())
@@ -260,20 +314,23 @@ def main():
         t0 = time.perf_counter()
         A2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
         B2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A2
-        C2 = ctx.spgemm(A2, B2, panel=panel)
-        chk = C2.checksum()
+        chk = [0.0, 0.0]
+        for pn in panels:
+            C2 = ctx.spgemm(A2, B2, panel=pn)
+            s_, a_ = C2.checksum()
+            chk[0] += s_; chk[1] += a_
+            C2.free()
         ctx.sync()
         ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         e2e_ms.append(float(ms.item()))
-        C2.free()
         if B2 is not A2:
             B2.free()
         A2.free()
     e2e_t = float(np.mean(e2e_ms[1:])) if len(e2e_ms) > 1 else e2e_ms[0]
     h2d = int(I.nbytes + J.nbytes + V.nbytes) * (2 if tb else 1)
-    d2h = 2 * 1024 * 2 * 8 + 3 * 8 * 16     # checksum partials + the size read-backs of one step
+    d2h = (2 * 1024 * 2 * 8 + 3 * 8 * 16) * sub     # checksum partials + the size read-backs of one step
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -301,7 +358,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": CONFIG_TEXT[args.config], "product": "A*A^T" if tb else "A^2",
                        "flop": flop, "nnz_A": int(ai.nnz), "nnz_C": c_nnz, "C_tiles": c_tiles, "tile_pairs": c_pairs,
-                       "parallelism": f"tile-row panels x{world}, B replicated",
+                       "parallelism": f"tile-row panels x{world}, B replicated" + (f"; {sub} sequential sub-panels per GPU" if sub > 1 else ""),
                        "l2": "no flush: each step streams > 1 GB (C + C' metadata), far above the 126 MB L2",
                        "keep_empty_tiles": args.keep_empty},
             "step_ms": step_t, "kernel_ms": kern_t,

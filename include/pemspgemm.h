@@ -135,7 +135,8 @@ typedef enum pem_tiled_array {
     PEM_T_TILE_COL_IDX = 6, /* int32   [tiles]    _X_tileColIdx    */
     PEM_T_TILE_ROW_IDX = 7, /* int32   [tiles]    tile row of each tile */
     PEM_T_COL_OCC = 8,      /* uint16  [tiles]    OR of the tile's row masks    */
-    PEM_T_ROW_OCC = 9       /* uint16  [tiles]    OR of the tile's column masks */
+    PEM_T_ROW_OCC = 9,      /* uint16  [tiles]    OR of the tile's column masks */
+    PEM_T_ROW_COL_IDX = 10  /* uint8   [nnz]      *tiles_rowColIdx: (r<<4)|c per value (spgemm.cu:195,221) */
 } pem_tiled_array;
 int pem_tiled_get(pem_ctx* ctx, const pem_tiled* t, int which, void* host_dst, size_t bytes);
 /* Device pointer of the same arrays (no copy; owned by the handle). */

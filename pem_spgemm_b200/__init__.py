@@ -32,7 +32,7 @@ T_ARRAYS = {
     "vals": (0, np.float64), "tile_nnz_ptr": (1, np.uint32), "masks": (2, np.uint16),
     "row_ptr": (3, np.uint8), "masks_t": (4, np.uint16), "tile_row_ptr": (5, np.int32),
     "tile_col_idx": (6, np.int32), "tile_row_idx": (7, np.int32), "col_occ": (8, np.uint16),
-    "row_occ": (9, np.uint16),
+    "row_occ": (9, np.uint16), "row_col_idx": (10, np.uint8),
 }
 R_ARRAYS = {
     "row_ptr": (0, np.int64), "tile_row": (1, np.int32), "tile_col": (2, np.int32),
@@ -263,7 +263,7 @@ class Tiled:
         i = self.info
         n = {"vals": i.nnz, "tile_nnz_ptr": i.tiles + 1, "masks": i.tiles * 16, "row_ptr": i.tiles * 16,
              "masks_t": i.tiles * 16, "tile_row_ptr": i.tile_rows + 1, "tile_col_idx": i.tiles,
-             "tile_row_idx": i.tiles, "col_occ": i.tiles, "row_occ": i.tiles}[name]
+             "tile_row_idx": i.tiles, "col_occ": i.tiles, "row_occ": i.tiles, "row_col_idx": i.nnz}[name]
         out = np.empty(n, dt)
         self.ctx._check(load().pem_tiled_get(self.ctx._h, self._h, idx, _ptr(out), out.nbytes))
         return out

@@ -56,6 +56,14 @@ k_make_keys(const int32_t* __restrict__ I, const int32_t* __restrict__ J, int64_
     }
 }
 
+// (r<<4)|c of every value = low byte of its sorted key
+__global__ void __launch_bounds__(256)
+k_rc_idx(const uint64_t* __restrict__ keys, int64_t nnz, uint8_t* __restrict__ rc)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) rc[e] = (uint8_t)(keys[e] & 255u);
+}
+
 // predicate for the tile census: position e starts a new tile
 struct HeadPred {
     const uint64_t* keys;
@@ -357,6 +365,10 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         CV_TRY(pem_alloc(ctx, &T->tile_row_idx, n));
         CV_TRY(pem_alloc(ctx, &T->col_occ, n));
         CV_TRY(pem_alloc(ctx, &T->row_occ, n));
+        CV_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)nnz));
+        k_rc_idx<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(keys_sorted, nnz, T->rc_idx);
+        ++ctx->launches;
+        CV_CK(cudaGetLastError());
         CV_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         k_build_tiles<<<pem_div_up(cnt, 128), 128, 0, ctx->stream>>>(
             keys_sorted, T->tile_nnz_ptr, (int)cnt, (uint32_t)nnz, cb, T->tile_rows, T->masks, T->masks_t,
@@ -375,6 +387,7 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         CV_TRY(pem_alloc(ctx, &T->vals, 0)); CV_TRY(pem_alloc(ctx, &T->masks, 0)); CV_TRY(pem_alloc(ctx, &T->masks_t, 0));
         CV_TRY(pem_alloc(ctx, &T->row_ptr, 0)); CV_TRY(pem_alloc(ctx, &T->tile_col_idx, 0));
         CV_TRY(pem_alloc(ctx, &T->tile_row_idx, 0)); CV_TRY(pem_alloc(ctx, &T->col_occ, 0)); CV_TRY(pem_alloc(ctx, &T->row_occ, 0));
+        CV_TRY(pem_alloc(ctx, &T->rc_idx, 0));
         CV_CK(cudaStreamSynchronize(ctx->stream));
     }
 #undef CV_TRY

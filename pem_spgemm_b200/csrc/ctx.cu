@@ -13,12 +13,15 @@
 // ---- caching allocator -----------------------------------------------------------------------
 // Replaces the reference's per-iteration cudaMallocAsync + 11 blocking cudaFree (spgemm.cu:1118-1131,
 // 1138-1295; its malloc_time).  Blocks come from the context's cudaMemPool_t once and are then
-// recycled by size: a block serves a request of up to its own size and no less than 3/4 of it.
+// recycled by size: a block serves a request of up to its own size and no less than half of it
+// (sequential tile-row panels of one product ask for similar, not equal, sizes).  Cached blocks are
+// only handed back to the driver when an allocation fails or the cache outgrows 80 % of the device:
+// unmapping and re-mapping tens of GB costs seconds, far more than any kernel here.
 int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
 {
     bytes = (bytes + 511) & ~(size_t)511;
     auto it = ctx->free_blocks.lower_bound(bytes);
-    if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 4) {
+    if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 2) {
         *p = it->second;
         ctx->live_blocks[*p] = it->first;
         ctx->cached_bytes -= it->first;
@@ -97,7 +100,7 @@ int pem_ctx_create(pem_ctx** out, int device)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit = total_b / 4;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit = total_b / 5 * 4;
     *out = ctx;
     return PEM_OK;
 }
@@ -189,6 +192,7 @@ static const void* tiled_array(const pem_tiled* t, int which, size_t* bytes)
         case PEM_T_TILE_ROW_IDX: *bytes = n * 4; return t->tile_row_idx;
         case PEM_T_COL_OCC: *bytes = n * 2; return t->col_occ;
         case PEM_T_ROW_OCC: *bytes = n * 2; return t->row_occ;
+        case PEM_T_ROW_COL_IDX: *bytes = (size_t)t->nnz; return t->rc_idx;
     }
     *bytes = 0;
     return nullptr;
@@ -205,7 +209,7 @@ int pem_tiled_get(pem_ctx* ctx, const pem_tiled* t, int which, void* host_dst, s
     if (!ctx || !t || !host_dst) return PEM_ERR_ARG;
     size_t have = 0;
     const void* src = tiled_array(t, which, &have);
-    if (!src && have == 0 && which > PEM_T_ROW_OCC) return ctx->fail(PEM_ERR_ARG, "unknown tiled array");
+    if (!src && have == 0 && which > PEM_T_ROW_COL_IDX) return ctx->fail(PEM_ERR_ARG, "unknown tiled array");
     if (bytes != have) return ctx->fail(PEM_ERR_ARG, "pem_tiled_get: size mismatch");
     if (bytes == 0) return PEM_OK;
     PEM_CK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -219,7 +223,7 @@ void pem_tiled_free(pem_ctx* ctx, pem_tiled* t)
     pem_free(ctx, t->vals); pem_free(ctx, t->tile_nnz_ptr); pem_free(ctx, t->masks);
     pem_free(ctx, t->masks_t); pem_free(ctx, t->row_ptr); pem_free(ctx, t->tile_row_ptr);
     pem_free(ctx, t->tile_col_idx); pem_free(ctx, t->tile_row_idx); pem_free(ctx, t->col_occ);
-    pem_free(ctx, t->row_occ); pem_free(ctx, t->srow_ptr); pem_free(ctx, t->srow_tile);
+    pem_free(ctx, t->row_occ); pem_free(ctx, t->rc_idx); pem_free(ctx, t->srow_ptr); pem_free(ctx, t->srow_tile);
     delete t;
 }
 

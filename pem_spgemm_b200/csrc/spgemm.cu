@@ -219,9 +219,12 @@ k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t
 }
 
 // step 2, kernel 1 (pair-owner).  Lane = pair:
-//   prod[r] = OR over k in Amask[r] of Bmask[k]            (16x16 boolean product, 8 registers)
+//   prod[r] = OR over k in Arow[r] of Bmask[k]             (16x16 boolean product)
 //   hit     = (rows with prod != 0) << 16 | (OR of prod)    which C rows / columns the pair touches
-// The hit words of 32 consecutive pairs are bit-transposed with 32 ballots and stored as one
+// The lane walks the A tile's nonzero list ((r<<4)|k bytes, the reference's *tiles_rowColIdx): one
+// 2-byte B mask load and one shared-memory OR per A nonzero, no per-row loops, so a warp's trip
+// count is the largest A tile among its 32 pairs instead of 16 x the largest row.
+// The hit words of 32 consecutive pairs are bit-transposed (5 butterfly shuffles) and stored as one
 // 32-word block: word 16+r (resp. c) of block b has bit i set iff pair 32b+i touches C row r
 // (resp. column c).  Step 3 ANDs two of those words to find the pairs feeding an entry (r, c)
 // without walking the list.
@@ -231,10 +234,14 @@ k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t
 __global__ void __launch_bounds__(S2P_THREADS)
 k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
               const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-              const uint16_t* __restrict__ Amasks, const uint16_t* __restrict__ Bmasks,
+              const uint32_t* __restrict__ A_off, const uint8_t* __restrict__ A_rc,
+              const uint16_t* __restrict__ A_masks_t,
+              const uint32_t* __restrict__ B_off, const uint8_t* __restrict__ B_rc,
+              const uint16_t* __restrict__ Bmasks,
               uint32_t* __restrict__ Cmasks32, uint32_t* __restrict__ hit_t)
 {
     __shared__ int s_ptr[S2P_THREADS + 2];
+    __shared__ unsigned s_acc[8 * S2P_THREADS];     // word w of thread t at [w * THREADS + t]: conflict-free
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t i0 = (int64_t)blockIdx.x * S2P_THREADS;
     const int64_t t_lo = blk_tile[blockIdx.x];
@@ -244,6 +251,8 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
         const int64_t rel = pair_ptr[t_lo + x] - i0;
         s_ptr[x] = (int)max((int64_t)-0x40000000, min(rel, (int64_t)0x40000000));
     }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_acc[w * S2P_THREADS + tid] = 0u;
     __syncthreads();
     const int64_t i = i0 + tid;
     const bool valid = i < n_pairs;
@@ -257,38 +266,67 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
         x = lo;
     }
     const int seg_s = valid ? s_ptr[x] : tid, seg_e = valid ? s_ptr[x + 1] : tid + 1;   // run of this tile, block-relative
+    // Two ways to form the product, chosen per pair by the shorter nonzero list:
+    //   by A's nonzeros (r,k):  prod[r] |= Bmask[k]                 (shared-memory OR, one per A nonzero)
+    //   by B's nonzeros (k,c):  prod[r] |= 1 << c for r in AcolMask[k]   (registers; a hub A tile times
+    //                           an ordinary B tile costs 1-2 steps instead of up to 256)
     unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned hit = 0;
+    bool by_b = false;
     if (valid) {
         const int2 ab = pairs[i];
-        const uint4* am4 = reinterpret_cast<const uint4*>(Amasks + (size_t)(unsigned)ab.x * 16u);
-        const uint4 ax = am4[0], ay = am4[1];
-        const unsigned aw[8] = {ax.x, ax.y, ax.z, ax.w, ay.x, ay.y, ay.z, ay.w};
-        const uint16_t* __restrict__ bm = Bmasks + (size_t)(unsigned)ab.y * 16u;
-        unsigned rows_hit = 0, cols_hit = 0;
+        const uint32_t a0 = A_off[ab.x], a1 = A_off[ab.x + 1];
+        const uint32_t b0 = B_off[ab.y], b1 = B_off[ab.y + 1];
+        by_b = 8u * (b1 - b0) < (a1 - a0);      // ~48 instructions per B nonzero against ~16 per A nonzero, and a warp pays for both paths
+        if (by_b) {
+            const uint16_t* __restrict__ at = A_masks_t + (size_t)(unsigned)ab.x * 16u;
+            for (uint32_t e = b0; e < b1; ++e) {
+                const unsigned kc = B_rc[e];
+                const unsigned rows = at[kc >> 4];           // rows of A holding column k
+                const unsigned c = kc & 15u;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            unsigned m = (aw[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
-            unsigned o = 0;
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                o |= bm[k];
+                for (int w = 0; w < 8; ++w) {
+                    const unsigned two = (rows >> (2 * w)) & 3u;          // rows 2w, 2w+1
+                    acc[w] |= ((two & 1u) | ((two & 2u) << 15)) << c;
+                }
             }
-            acc[r >> 1] |= o << ((r & 1) * 16);
-            cols_hit |= o;
-            rows_hit |= (o ? 1u : 0u) << r;
+        } else {
+            const uint16_t* __restrict__ bm = Bmasks + (size_t)(unsigned)ab.y * 16u;
+            unsigned* my = s_acc + tid;
+#pragma unroll 2
+            for (uint32_t e = a0; e < a1; ++e) {
+                const unsigned rc = A_rc[e];
+                const unsigned o = bm[rc & 15u];
+                const unsigned r = rc >> 4;
+                my[(r >> 1) * S2P_THREADS] |= o << ((r & 1u) * 16u);
+            }
         }
-        hit = (rows_hit << 16) | cols_hit;
     }
-    // 32x32 bit transpose of the warp's hit words
-    unsigned mine = 0;
+    if (!by_b) {
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-        const unsigned w = __ballot_sync(0xffffffffu, (hit >> b) & 1u);
-        mine = lane == b ? w : mine;
+        for (int w = 0; w < 8; ++w) acc[w] = s_acc[w * S2P_THREADS + tid];
     }
-    if (i0 + (tid & ~31) < n_pairs) hit_t[i0 + tid] = mine;
+    unsigned hit = 0;
+    {
+        unsigned c = 0, rows_hit = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            c |= acc[w];
+            rows_hit |= ((acc[w] & 0xFFFFu) ? 1u : 0u) << (2 * w);
+            rows_hit |= ((acc[w] >> 16) ? 1u : 0u) << (2 * w + 1);
+        }
+        hit = (rows_hit << 16) | ((c | (c >> 16)) & 0xFFFFu);
+    }
+    // 32x32 bit transpose across the warp: afterwards lane b holds bit b of every lane's hit word
+    {
+        unsigned v = hit, m = 0x0000FFFFu;
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const unsigned y = __shfl_xor_sync(0xffffffffu, v, j);
+            v = (lane & j) ? ((v & ~m) | ((y >> j) & m)) : ((v & ~(m << j)) | ((y & m) << j));
+            m ^= m << (j >> 1);
+        }
+        if (i0 + (tid & ~31) < n_pairs) hit_t[i0 + tid] = v;
+    }
     // segmented inclusive OR scan along the lanes of a tile's run
     const int wfirst = tid & ~31;
 #pragma unroll
@@ -545,8 +583,8 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
             PEM_LAUNCHED();
             KT_BEGIN(KT_PAIRS);
             k_step2_pairs<<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(
-                C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->masks, B->masks,
-                reinterpret_cast<uint32_t*>(C->masks), C->pair_hit);
+                C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->tile_nnz_ptr, A->rc_idx, A->masks_t,
+                B->tile_nnz_ptr, B->rc_idx, B->masks, reinterpret_cast<uint32_t*>(C->masks), C->pair_hit);
             KT_END(KT_PAIRS);
             PEM_LAUNCHED();
             pem_free(ctx, blk);

@@ -31,6 +31,7 @@ def _check_tiled(T, O):
     assert np.array_equal(T.array("masks").reshape(-1, 16), O.masks)
     assert np.array_equal(T.array("masks_t").reshape(-1, 16), O.masks_t)
     assert np.array_equal(T.array("row_ptr").reshape(-1, 16), O.row_ptr)
+    assert np.array_equal(T.array("row_col_idx"), O.row_col_idx)
     assert np.array_equal(T.array("tile_row_ptr"), O.tile_row_ptr)
     assert np.array_equal(T.array("tile_col_idx"), O.tile_col)
     assert np.array_equal(T.array("tile_row_idx"), O.tile_row)

@@ -238,6 +238,48 @@ k_srow_fill(int tile_rows, const int32_t* __restrict__ tile_row_ptr, const uint1
     }
 }
 
+// ---- step-3 views (see pem_tiled::row_rec) -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_row_rec(const uint16_t* __restrict__ masks, const uint8_t* __restrict__ row_ptr, int64_t n, uint32_t* __restrict__ rec)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rec[i] = (uint32_t)masks[i] | ((uint32_t)row_ptr[i] << 16);
+}
+
+// thread per tile: column pointers from the column masks, then every value goes to its column-major slot
+__global__ void __launch_bounds__(128)
+k_col_views(int cnt, const uint32_t* __restrict__ tile_nnz_ptr, const uint16_t* __restrict__ masks_t,
+            const uint8_t* __restrict__ rc_idx, const double* __restrict__ vals,
+            uint32_t* __restrict__ col_rec, double* __restrict__ vals_t)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const uint4* m4 = reinterpret_cast<const uint4*>(masks_t + (size_t)t * 16);
+    const uint4 a = m4[0], b = m4[1];
+    const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    unsigned rec[16];
+    unsigned run = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const unsigned m = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+        rec[c] = m | (run << 16);
+        run += __popc(m);
+    }
+    uint4* out = reinterpret_cast<uint4*>(col_rec + (size_t)t * 16);
+    out[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
+    out[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
+    out[2] = make_uint4(rec[8], rec[9], rec[10], rec[11]);
+    out[3] = make_uint4(rec[12], rec[13], rec[14], rec[15]);
+    const uint32_t s = tile_nnz_ptr[t], e = tile_nnz_ptr[t + 1];
+    const uint32_t* my = col_rec + (size_t)t * 16;      // just written by this thread
+    for (uint32_t x = s; x < e; ++x) {
+        const unsigned rc = rc_idx[x];
+        const unsigned r = rc >> 4, c = rc & 15u;
+        const unsigned cr = my[c];
+        vals_t[s + (cr >> 16) + __popc(cr & ((1u << r) - 1u))] = vals[x];
+    }
+}
+
 bool is_device_ptr(const void* p)
 {
     cudaPointerAttributes at;
@@ -432,6 +474,36 @@ int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* Bc)
     B->srow_ptr = ptr;
     B->srow_total = total;
     B->srow_tile = tl;
+    return PEM_OK;
+}
+
+// Step-3 views of a tiled matrix, built once per role and cached on the handle.
+int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* Tc, bool as_a, bool as_b)
+{
+    pem_tiled* T = const_cast<pem_tiled*>(Tc);
+    const size_t n16 = (size_t)T->tiles * 16;
+    if (as_a && !T->row_rec) {
+        uint32_t* rec = nullptr;
+        PEM_TRY(pem_alloc(ctx, &rec, n16));
+        if (n16) {
+            k_row_rec<<<pem_div_up((int64_t)n16, 256), 256, 0, ctx->stream>>>(T->masks, T->row_ptr, (int64_t)n16, rec);
+            PEM_LAUNCHED();
+        }
+        T->row_rec = rec;
+    }
+    if (as_b && !T->col_rec) {
+        uint32_t* rec = nullptr;
+        double* vt = nullptr;
+        PEM_TRY(pem_alloc(ctx, &rec, n16));
+        PEM_TRY(pem_alloc(ctx, &vt, (size_t)T->nnz));
+        if (T->tiles) {
+            k_col_views<<<pem_div_up(T->tiles, 128), 128, 0, ctx->stream>>>(T->tiles, T->tile_nnz_ptr, T->masks_t, T->rc_idx,
+                                                                           T->vals, rec, vt);
+            PEM_LAUNCHED();
+        }
+        T->col_rec = rec;
+        T->vals_t = vt;
+    }
     return PEM_OK;
 }
 

@@ -116,6 +116,11 @@ struct pem_tiled {
     int64_t* srow_ptr = nullptr;      // [rows16+1], rows16 = 16*tile_rows
     int32_t* srow_tile = nullptr;     // [srow_ptr[rows16]]
     int64_t srow_total = 0;
+    // step-3 views, built on first use (pem_tiled_build_views): one 32-bit record per tile row /
+    // tile column = mask | first-value offset << 16, and the values in column-major order inside a tile
+    uint32_t* row_rec = nullptr;      // [tiles*16]  masks[i]   | row_ptr[i] << 16          (operand A)
+    uint32_t* col_rec = nullptr;      // [tiles*16]  masks_t[i] | first value of column << 16 (operand B)
+    double* vals_t = nullptr;         // [nnz] tile-major, column-major inside a tile        (operand B)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -161,3 +166,4 @@ int pem_scan_exclusive_i64(pem_ctx* ctx, int64_t* d_inout, int64_t n);  // in pl
 extern "C" int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C);
 int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C);  // step1_esc.cu
 int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* B);                              // convert.cu
+int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* T, bool as_a, bool as_b);       // convert.cu

@@ -394,10 +394,9 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
                 const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
                 const uint32_t* __restrict__ hit_t,
                 const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
-                const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
-                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
-                const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
-                const uint16_t* __restrict__ B_masks_t, double* __restrict__ C_vals)
+                const uint32_t* __restrict__ A_row_rec,
+                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals_t,
+                const uint32_t* __restrict__ B_col_rec, double* __restrict__ C_vals)
 {
     __shared__ int s_off[S3E_TMAX];
     const int tid = threadIdx.x;
@@ -429,7 +428,6 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
     }
     const unsigned rc = row_col_idx[n];
     const unsigned r = rc >> 4, c = rc & 15u;
-    const unsigned below_c = (1u << c) - 1u;
     const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
     double acc = 0.0;
     for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
@@ -441,18 +439,18 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
             const int64_t i = base + (__ffs(w) - 1);
             w &= w - 1;
             const int2 ab = pairs[i];
-            const unsigned ia = (unsigned)ab.x * 16u, ib = (unsigned)ab.y * 16u;
-            const unsigned am = A_masks[ia + r];
-            unsigned m = am & B_masks_t[ib + c];
+            // one record per A tile row / B tile column: mask | offset of its first value << 16
+            const unsigned ar = A_row_rec[(unsigned)ab.x * 16u + r];
+            const unsigned bc = B_col_rec[(unsigned)ab.y * 16u + c];
+            unsigned m = ar & bc & 0xFFFFu;
             if (m) {
-                const double* __restrict__ av = A_vals + (A_off[ab.x] + A_rowptr[ia + r]);
-                const double* __restrict__ bv = B_vals + B_off[ab.y];
+                const double* __restrict__ av = A_vals + (A_off[ab.x] + (ar >> 16));        // row r of the A tile
+                const double* __restrict__ bv = B_vals_t + (B_off[ab.y] + (bc >> 16));      // column c of the B tile
                 do {
-                    const unsigned k = __ffs(m) - 1;
-                    m &= m - 1;
-                    const unsigned ao = __popc(am & ((1u << k) - 1u));
-                    const unsigned bo = B_rowptr[ib + k] + __popc(B_masks[ib + k] & below_c);
-                    acc = fma(av[ao], bv[bo], acc);
+                    const unsigned low = m & (0u - m);
+                    m ^= low;
+                    const unsigned lt = low - 1u;                // lt < 2^16: the offset bits drop out of the ranks
+                    acc = fma(av[__popc(ar & lt)], bv[__popc(bc & lt)], acc);
                 } while (m);
             }
         }
@@ -636,12 +634,13 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
             B->masks_t, C->vals);
         PEM_LAUNCHED();
     } else if (C->nnz > 0 && C->pair_hit) {      // entry-owner variant (step 2 prepared its inputs)
+        PEM_TRY(pem_tiled_build_views(ctx, A, true, false));   // cached on the handles after the first product
+        PEM_TRY(pem_tiled_build_views(ctx, B, false, true));
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^39 nonzeros");
         k_step3_entries<<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(
             C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, C->row_col_idx, C->pair_ptr, C->pair_list, C->pair_hit,
-            A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr,
-            B->masks_t, C->vals);
+            A->tile_nnz_ptr, A->vals, A->row_rec, B->tile_nnz_ptr, B->vals_t, B->col_rec, C->vals);
         PEM_LAUNCHED();
     } else if (C->tiles > 0) {
         const int64_t nblk = (C->tiles * 16 + S3_THREADS - 1) / S3_THREADS;

@@ -145,7 +145,8 @@ const void* pem_tiled_device_ptr(const pem_tiled* t, int which);
 /* ---- flop count and panel partition ---------------------------------------------------- */
 /* flop = sum over a_ik of nnz(B row k); replaces the host thread at spgemm.cu:1068-1079. */
 int pem_count_flop(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, uint64_t* flop);
-/* Split A's tile rows into nparts contiguous panels with balanced flop: bounds[0]=0,
+/* Split A's tile rows into nparts contiguous panels of balanced work (per-tile-row flop + 16 x the
+ * tile products step 1 expands for the row, both counted on the device): bounds[0]=0,
  * bounds[nparts]=tile_rows (north_star: row-block tile-row panels by per-row flop count). */
 int pem_partition_panels(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, int nparts,
                          int32_t* bounds /* nparts+1 */);

@@ -23,10 +23,6 @@
 
 namespace {
 
-__device__ __forceinline__ int bits_for(int n)
-{  // bits needed to hold values 0..n-1 (at least 1)
-    return n <= 1 ? 1 : 32 - __clz(n - 1);
-}
 inline int h_bits_for(int64_t n)
 {
     int b = 1;
@@ -280,6 +276,30 @@ k_col_views(int cnt, const uint32_t* __restrict__ tile_nnz_ptr, const uint16_t* 
     }
 }
 
+// tile products of one A tile, at tile level (length of B's tile row) and through B's row slices;
+// the smaller of the two is what step 1 will expand.  Summed per tile row.
+__global__ void __launch_bounds__(256)
+k_tile_prodcost(const uint16_t* __restrict__ col_occ, const int32_t* __restrict__ tile_row,
+                const int32_t* __restrict__ tile_col, int cnt, const int32_t* __restrict__ Brp,
+                const int64_t* __restrict__ srow_ptr, unsigned long long* __restrict__ row_tile_cost,
+                unsigned long long* __restrict__ row_sliced_cost)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const int k = tile_col[t];
+    const unsigned long long pt = (unsigned long long)(Brp[k + 1] - Brp[k]);
+    unsigned occ = col_occ[t];
+    const int64_t* sp = srow_ptr + (size_t)k * 16;
+    unsigned long long ps = 0;
+    while (occ) {
+        const int c = __ffs(occ) - 1;
+        occ &= occ - 1;
+        ps += (unsigned long long)(sp[c + 1] - sp[c]);
+    }
+    if (pt) atomicAdd(&row_tile_cost[tile_row[t]], pt);
+    if (ps) atomicAdd(&row_sliced_cost[tile_row[t]], ps);
+}
+
 bool is_device_ptr(const void* p)
 {
     cudaPointerAttributes at;
@@ -531,19 +551,43 @@ int pem_partition_panels(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, i
     if (!ctx || !A || !B || !bounds || nparts <= 0) return PEM_ERR_ARG;
     if (A->cols != B->rows) return ctx->fail(PEM_ERR_ARG, "inner dimensions differ");
     PEM_CK(cudaSetDevice(ctx->device));
+    const size_t ntr = (size_t)A->tile_rows;
     unsigned long long* trf = nullptr;
     PEM_TRY(tile_row_flops(ctx, A, B, &trf));
-    std::vector<unsigned long long> h((size_t)A->tile_rows);
-    if (A->tile_rows) PEM_CK(cudaMemcpyAsync(h.data(), trf, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> h(ntr), hp(ntr, 0), hs(ntr, 0);
+    if (ntr) PEM_CK(cudaMemcpyAsync(h.data(), trf, ntr * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // Weight of a tile row = its flop (the reference's and the north star's measure, spgemm.cu:1068-1079)
+    // + 16 x the tile products step 1 will expand for it: steps 1 and 2 and the per-pair part of step 3
+    // cost per tile PAIR, not per flop, and on power-law inputs the two are distributed very differently
+    // (hub rows: many flops in few tiles; ordinary rows: one pair per C tile).
+    if (A->tiles && B->tiles) {
+        PEM_TRY(pem_tiled_build_srow(ctx, B));
+        unsigned long long *cp = nullptr, *cs = nullptr;
+        PEM_TRY(pem_alloc(ctx, &cp, ntr));
+        PEM_TRY(pem_alloc(ctx, &cs, ntr));
+        PEM_CK(cudaMemsetAsync(cp, 0, ntr * 8, ctx->stream));
+        PEM_CK(cudaMemsetAsync(cs, 0, ntr * 8, ctx->stream));
+        k_tile_prodcost<<<pem_div_up(A->tiles, 256), 256, 0, ctx->stream>>>(A->col_occ, A->tile_row_idx, A->tile_col_idx, A->tiles,
+                                                                          B->tile_row_ptr, B->srow_ptr, cp, cs);
+        PEM_LAUNCHED();
+        PEM_CK(cudaMemcpyAsync(hp.data(), cp, ntr * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PEM_CK(cudaMemcpyAsync(hs.data(), cs, ntr * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PEM_CK(cudaStreamSynchronize(ctx->stream));
+        pem_free(ctx, cp);
+        pem_free(ctx, cs);
+    }
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     pem_free(ctx, trf);
     unsigned long long total = 0;
-    for (auto v : h) total += v + 1;  // +1: rows without flop still cost a little and keep panels contiguous
+    for (size_t r = 0; r < ntr; ++r) {
+        h[r] += 16ull * std::min(hp[r], hs[r]) + 1;  // +1: empty rows still cost a little and keep panels contiguous
+        total += h[r];
+    }
     bounds[0] = 0;
     unsigned long long run = 0;
     int part = 1;
     for (int r = 0; r < A->tile_rows && part < nparts; ++r) {
-        run += h[(size_t)r] + 1;
+        run += h[(size_t)r];
         // close panel `part` once it has reached its share of the prefix
         while (part < nparts && run * (unsigned long long)nparts >= total * (unsigned long long)part) bounds[part++] = r + 1;
     }

@@ -1,7 +1,7 @@
 """Multi-GPU sharding of C = A*B: the host-side logic around the engine's panel entry points.
 
 The path shards by independent units: every tile row of C depends only on the same tile row of A
-and on (read-only, replicated) B.  A is cut into contiguous tile-row panels with balanced flop
+and on (read-only, replicated) B.  A is cut into contiguous tile-row panels with balanced work (flop + tile products)
 (`pem_partition_panels`, device-side flop count), each rank multiplies its panel with
 `pem_spgemm_panel`, and the ONLY exchange is an all-gather of three integers per rank
 {nnz(C shard), C' tiles, pairs}, whose exclusive scan gives every shard's offset in the global C

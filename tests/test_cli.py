@@ -1,0 +1,72 @@
+"""The drop-in process surface: `pemspgemm <mtx> [0/1] [1]` (reference: spgemm.cu:720-1568,
+README.md:39-53).  Argument handling is checked on CPU (it happens before any CUDA call); the
+report, CSV row and COO dump are checked on the GPU against the host oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pem_spgemm_b200 as pem
+from pem_spgemm_b200 import synth
+
+
+def _run(args, cwd, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([pem.CLI_PATH] + args, cwd=cwd, env=e, capture_output=True, text=True, timeout=300)
+
+
+def test_cli_usage_and_rectangular_messages(tmp_path):
+    assert os.path.exists(pem.CLI_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    out = _run([], tmp_path)                                    # spgemm.cu:722-725
+    assert out.returncode == 1 and "Provide a matrix market file path. Exiting." in out.stdout
+    out = _run(["a", "0", "1", "extra"], tmp_path)
+    assert out.returncode == 1 and "Provide a matrix market file path. Exiting." in out.stdout
+    rows, cols, I, J, V = synth.random_sparse(5, 9, 12, seed=1)
+    mtx = str(tmp_path / "rect.mtx")
+    pem.mtx_write(mtx, rows, cols, I, J, V)
+    out = _run([mtx, "0"], tmp_path)                            # spgemm.cu:782-786
+    assert out.returncode == 1 and "input is rectangular. Only AAt is possible. Exiting." in out.stdout
+    out = _run([str(tmp_path / "missing.mtx"), "0"], tmp_path)  # the reference would crash; we report
+    assert out.returncode == 2 and "cannot read" in out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("aat", [False, True])
+def test_cli_report_csv_and_dump(tmp_path, aat):
+    from oracle import host
+    if aat:
+        rows, cols, I, J, V = synth.random_sparse(70, 300, 1500, seed=5)
+    else:
+        rows, cols, I, J, V = synth.laplacian2d(24)
+    os.makedirs(tmp_path / "in")
+    mtx = str(tmp_path / "in" / "case_a.mtx")
+    pem.mtx_write(mtx, rows, cols, I, J, V)
+    env = {"PEM_DUMP_DIR": str(tmp_path), "PEM_REPEAT": "2", "PEM_WARMUP": "1"}
+    out = _run([mtx, "1"] + (["1"] if aat else []), tmp_path, env)
+    assert out.returncode == 0, out.stderr
+    oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, aat)
+    ro, co, vo = oC.to_coo()
+    flop = host.flop(oA, oB)
+    # report lines (spgemm.cu:1406-1422)
+    for needle in ("<---Program done--->", f"Flop count: {flop}", f"C nnz: {ro.size}", "pemSpGEMM took",
+                   "Saving results to", "CLEANING UP RESOURCES"):
+        assert needle in out.stdout, needle
+    # COO dump (spgemm.cu:1527-1560): NNZ without newline, 0-based rows/cols, values with 17 digits
+    assert open(tmp_path / "SPGEMM_RESULT_NNZ.txt").read() == str(ro.size)
+    r = np.loadtxt(tmp_path / "SPGEMM_RESULT_ROWS.txt", dtype=np.int64, ndmin=1)
+    c = np.loadtxt(tmp_path / "SPGEMM_RESULT_COLS.txt", dtype=np.int64, ndmin=1)
+    v = np.loadtxt(tmp_path / "SPGEMM_RESULT_VALS.txt", dtype=np.float64, ndmin=1)
+    assert np.array_equal(r, ro) and np.array_equal(c, co)
+    np.testing.assert_allclose(v, vo, rtol=1e-12, atol=1e-16)   # std::fixed, 17 decimals
+    # CSV (spgemm.cu:1424-1450, README.md:51-53): one row, preceded by a newline, 14 fields, no header
+    raw = open(tmp_path / "pemspgemm_benchmark_result.csv").read()
+    assert raw.startswith("\n") and raw.count("\n") == 1
+    f = raw.strip().split(",")
+    assert len(f) == 14 and f[0] == "case_a" and int(f[1]) == flop and int(f[2]) == ro.size
+    assert f[3] == f"{flop / ro.size:.2f}"
+    assert all(len(x.split(".")[1]) == 2 for x in f[3:])
+    out = _run([mtx, "0"] + (["1"] if aat else []), tmp_path, env)      # second run appends
+    assert out.returncode == 0 and "Not saving results. Exiting." in out.stdout
+    assert open(tmp_path / "pemspgemm_benchmark_result.csv").read().count("\n") == 2

@@ -284,7 +284,7 @@ void pem_result_free(pem_ctx* ctx, pem_result* C)
 {
     if (!ctx || !C) return;
     pem_free(ctx, C->row_ptr); pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col);
-    pem_free(ctx, C->pair_ptr); pem_free(ctx, C->pair_list); pem_free(ctx, C->pair_hit); pem_free(ctx, C->blk_tile);
+    pem_free(ctx, C->pair_ptr); pem_free(ctx, C->pair_list); pem_free(ctx, C->pair_hit); pem_free(ctx, C->blk_tile); pem_free(ctx, C->pair_blk);
     pem_free(ctx, C->masks); pem_free(ctx, C->tile_nnz_ptr); pem_free(ctx, C->row_col_idx);
     pem_free(ctx, C->vals);
     delete C;

@@ -143,6 +143,7 @@ struct pem_result {
     uint8_t* row_col_idx = nullptr;   // [nnz], produced on demand (pem_result_make_rowcolidx)
     uint32_t* pair_hit = nullptr;     // [pairs] entry-owner variant: (C rows hit << 16) | C columns hit by the pair
     int32_t* blk_tile = nullptr;      // entry-owner variant: first tile of each 256-entry step-3 block
+    int32_t* pair_blk = nullptr;      // first tile of each 256-pair step-2 block (optional by-product of step 1)
     double* vals = nullptr;           // [nnz]
 };
 

@@ -390,7 +390,7 @@ constexpr int S3E_TMAX = 512;
 
 __global__ void __launch_bounds__(S3E_ENTRIES)
 k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
-                const int64_t* __restrict__ c_tile_nnz_ptr, const uint8_t* __restrict__ row_col_idx,
+                const int64_t* __restrict__ c_tile_nnz_ptr, const uint32_t* __restrict__ Cmasks32,
                 const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
                 const uint32_t* __restrict__ hit_t,
                 const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
@@ -411,6 +411,7 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
     const int64_t n = n0 + tid;
     if (n >= nnz) return;
     int64_t t;
+    int e;                                          // rank of this nonzero inside its tile
     if (staged) {                                   // last i with s_off[i] <= tid
         int lo = 0, hi = (int)span - 1;
         while (lo < hi) {
@@ -418,6 +419,7 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
             if (s_off[mid] <= tid) lo = mid; else hi = mid - 1;
         }
         t = t0 + lo;
+        e = tid - s_off[lo];
     } else {                                        // many empty tiles in range (keep_empty mode)
         int64_t lo = t0, hi = t1;
         while (lo < hi) {
@@ -425,9 +427,38 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
             if (c_tile_nnz_ptr[mid] <= n) lo = mid; else hi = mid - 1;
         }
         t = lo;
+        e = (int)(n - c_tile_nnz_ptr[t]);
     }
-    const unsigned rc = row_col_idx[n];
-    const unsigned r = rc >> 4, c = rc & 15u;
+    // (r, c) = position of the e-th set bit of the tile's 256-bit mask (word w = rows 2w, 2w+1), which
+    // is what Ctiles_rowColIdx[n] would hold (spgemm.cu:552-591) without materialising that array
+    unsigned r, c;
+    {
+        const uint4* m4 = reinterpret_cast<const uint4*>(Cmasks32 + (size_t)t * 8);
+        const uint4 x = m4[0], y = m4[1];
+        const unsigned w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        unsigned sel = 0, wi = 0;
+        int rem = e;
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int pc = __popc(w[i]);
+            const bool here = !done && rem < pc;
+            sel = here ? w[i] : sel;
+            wi = here ? (unsigned)i : wi;
+            done = done || here;
+            rem -= done ? 0 : pc;
+        }
+        unsigned b = 0;                             // position of the rem-th set bit of sel: 5 halving steps
+#pragma unroll
+        for (int width = 16; width > 0; width >>= 1) {
+            const int pc = __popc(sel & (((1u << width) - 1u) << b));
+            const bool up = rem >= pc;
+            rem -= up ? pc : 0;
+            b += up ? (unsigned)width : 0u;
+        }
+        r = 2u * wi + (b >> 4);
+        c = b & 15u;
+    }
     const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
     double acc = 0.0;
     for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
@@ -575,10 +606,13 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
         PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)nblk * S2P_THREADS));
         PEM_CK(cudaMemsetAsync(C->masks, 0, (size_t)C->tiles * 32, ctx->stream));
         if (C->pairs > 0) {
-            int32_t* blk = nullptr;
-            PEM_TRY(pem_alloc(ctx, &blk, (size_t)nblk + 1));
-            k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
-            PEM_LAUNCHED();
+            int32_t* blk = C->pair_blk;            // expand-sort-compress leaves it behind (k_ctiles)
+            C->pair_blk = nullptr;
+            if (!blk) {
+                PEM_TRY(pem_alloc(ctx, &blk, (size_t)nblk + 1));
+                k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
+                PEM_LAUNCHED();
+            }
             KT_BEGIN(KT_PAIRS);
             k_step2_pairs<<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(
                 C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->tile_nnz_ptr, A->rc_idx, A->masks_t,
@@ -606,8 +640,7 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     // (measured on B200, profiles/: the entry-owner kernel wins on every BASELINE config, including the
     // stencil matrix with ~30 nonzeros per C tile, so the tile-owner kernel is opt-in)
     C->s3_tiles = ctx->opt_owner == 3;
-    if (!rows_variant && !C->s3_tiles) {   // what the entry-owner step 3 reads: (r,c) per nonzero, first tile per block
-        PEM_TRY(pem_result_make_rowcolidx(ctx, C));
+    if (!rows_variant && !C->s3_tiles) {   // what the entry-owner step 3 reads: first tile of every 256-nonzero block
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
         if (C->tiles > 0) {
@@ -639,7 +672,7 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^39 nonzeros");
         k_step3_entries<<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(
-            C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, C->row_col_idx, C->pair_ptr, C->pair_list, C->pair_hit,
+            C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, reinterpret_cast<const uint32_t*>(C->masks), C->pair_ptr, C->pair_list, C->pair_hit,
             A->tile_nnz_ptr, A->vals, A->row_rec, B->tile_nnz_ptr, B->vals_t, B->col_rec, C->vals);
         PEM_LAUNCHED();
     } else if (C->tiles > 0) {

@@ -297,11 +297,16 @@ template <class KeyT>
 __global__ void __launch_bounds__(256)
 k_ctiles(int64_t ntiles, int64_t npairs, int nrows, int rb, int wbits, const KeyT* __restrict__ keys,
          const int64_t* __restrict__ heads, const int* __restrict__ jmin, int64_t* __restrict__ pair_ptr,
-         int32_t* __restrict__ tile_row, int32_t* __restrict__ tile_col, int64_t* __restrict__ row_ptr)
+         int32_t* __restrict__ tile_row, int32_t* __restrict__ tile_col, int64_t* __restrict__ row_ptr,
+         int32_t* __restrict__ pair_blk)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     const int64_t h = heads[t];
+    {   // first tile of every 256-pair block of step 2 (a tile owning pairs [h, hn) opens the blocks that start inside)
+        const int64_t hn = t + 1 < ntiles ? heads[t + 1] : npairs;
+        for (int64_t b = (h + 255) / 256; b * 256 < hn; ++b) pair_blk[b] = (int32_t)t;
+    }
     const KeyT key = keys[h];
     const int row = (int)(key >> wbits);
     const int jrel = (int)(key & (((KeyT)1 << wbits) - 1));
@@ -443,8 +448,10 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     E_TRY(pem_alloc(ctx, &C->tile_row, (size_t)T));
     E_TRY(pem_alloc(ctx, &C->tile_col, (size_t)T));
     E_TRY(pem_alloc(ctx, &C->pair_ptr, (size_t)T + 1));
+    pem_free(ctx, C->pair_blk);
+    E_TRY(pem_alloc(ctx, &C->pair_blk, (size_t)((F + 255) / 256) + 1));
     k_ctiles<KeyT><<<pem_div_up(T, 256), 256, 0, ctx->stream>>>(T, F, nrows, rb, wbits, key_a, heads, jmin, C->pair_ptr,
-                                                                C->tile_row, C->tile_col, C->row_ptr);
+                                                                C->tile_row, C->tile_col, C->row_ptr, C->pair_blk);
     E_LAUNCHED();
     C->pair_list = val_a;
     val_a = nullptr;

@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include "engine.cuh"
 
@@ -59,6 +60,7 @@ k_tile_products(int p0, int np, int rb, const int32_t* __restrict__ Acol, const 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cost = 0, items = 0;
+    int row = -1, lo = INT_MAX, hi = -1;
     if (i < np) {
         const int p = p0 + i;
         const int k = Acol[p];
@@ -66,10 +68,9 @@ k_tile_products(int p0, int np, int rb, const int32_t* __restrict__ Acol, const 
         plen[i] = be - bs;
         bfirst[i] = bs;
         if (be > bs) {
-            const int row = Arow[p] - rb;
-            const int lo = Bcol[bs], hi = Bcol[be - 1];
-            if (lo < jmin[row]) atomicMin(&jmin[row], lo);
-            if (hi > jmax[row]) atomicMax(&jmax[row], hi);
+            row = Arow[p] - rb;
+            lo = Bcol[bs];
+            hi = Bcol[be - 1];
         }
         if (srow_ptr) {            // cost of expanding this tile through B's row slices instead
             unsigned occ = AcolOcc[p];
@@ -85,6 +86,15 @@ k_tile_products(int p0, int np, int rb, const int32_t* __restrict__ Acol, const 
     } else if (i == np) {
         plen[i] = 0;
         if (srow_ptr) icnt[i] = 0;
+    }
+    {   // window of reachable tile columns per C' row: the tiles of a row are consecutive threads, so the
+        // lanes of one row reduce among themselves and their leader issues the two atomics
+        const unsigned peers = __match_any_sync(0xffffffffu, row);
+        const int wlo = __reduce_min_sync(peers, lo), whi = __reduce_max_sync(peers, hi);
+        if (row >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) {
+            if (wlo < jmin[row]) atomicMin(&jmin[row], wlo);
+            if (whi > jmax[row]) atomicMax(&jmax[row], whi);
+        }
     }
     if (srow_ptr) {
 #pragma unroll
@@ -369,7 +379,10 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     size_t free_b = 0, total_b = 0;
     E_CK(cudaMemGetInfo(&free_b, &total_b));
     const size_t staged_bytes = (size_t)P * (sizeof(KeyT) + sizeof(int2));
-    const bool staged = staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
+    // (PEM_ESC_TWO_PASS=1 forces the count-then-write variant; tests use it, nothing else should)
+    const char* force2 = getenv("PEM_ESC_TWO_PASS");
+    const bool staged = !(force2 && *force2 == '1') &&
+                        staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
     int64_t F = 0;
     if (staged) {
         E_TRY(pem_alloc(ctx, &key_b, (size_t)P));

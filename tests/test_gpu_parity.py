@@ -266,3 +266,53 @@ def test_step1_paths_agree_at_full_size(engine, k, esc):
     if B is not A:
         B.free()
     A.free()
+
+
+def test_wide_index_space_uses_64bit_sort_keys(engine):
+    """16.7M x 16.7M with the nonzeros on ~3000 scattered rows/columns: ~1M tile rows and a tile-column
+    window of ~1M need 40 key bits, i.e. the 64-bit-key instantiation of expand-sort-compress."""
+    rng = np.random.default_rng(7)
+    n = 1 << 24
+    ids = np.sort(rng.choice(n, size=3000, replace=False)).astype(np.int64)
+    I = ids[rng.integers(0, ids.size, 120_000)]
+    J = ids[rng.integers(0, ids.size, 120_000)]
+    key = np.unique(I * n + J)
+    I = (key // n).astype(np.int32); J = (key % n).astype(np.int32)
+    V = rng.uniform(-1, 1, I.size)
+    _, _, oC = host.spgemm_from_coo(n, n, I, J, V, False)
+    A = engine.convert_coo(n, n, I, J, V)
+    for path in (3, 4):
+        engine.set_option(pem.OPT_STEP1_PATH, path)
+        try:
+            C = engine.spgemm(A, A)
+        finally:
+            engine.set_option(pem.OPT_STEP1_PATH, 0)
+        _assert_same_C(C, oC)
+        C.free()
+    A.free()
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_esc_count_then_write_variant(engine, k):
+    """The variant of expand-sort-compress used when product-sized staging buffers would not fit
+    (count per chunk, scan, write exactly): same arrays as the staged variant."""
+    import os
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    got = {}
+    for two_pass in ("0", "1"):
+        os.environ["PEM_ESC_TWO_PASS"] = two_pass
+        try:
+            for path in (3, 4):
+                engine.set_option(pem.OPT_STEP1_PATH, path)
+                C = engine.spgemm(A, A)
+                got[(two_pass, path)] = [C.array(x) for x in ("row_ptr", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "vals")]
+                C.free()
+        finally:
+            os.environ.pop("PEM_ESC_TWO_PASS", None)
+            engine.set_option(pem.OPT_STEP1_PATH, 0)
+    ref = got[("0", 3)]
+    for key, arrs in got.items():
+        for a, b in zip(ref, arrs):
+            assert np.array_equal(a, b), key
+    A.free()

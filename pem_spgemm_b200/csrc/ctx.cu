@@ -5,6 +5,7 @@
 // 1118-1131) are pool hits and leave the critical path.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -37,6 +38,7 @@ int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
     }
     if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
     ctx->live_blocks[*p] = bytes;
+    ctx->pool_taken += bytes;
     return PEM_OK;
 }
 
@@ -54,7 +56,10 @@ void pem_free_bytes(pem_ctx* ctx, void* p)
 
 void pem_cache_release(pem_ctx* ctx)
 {
-    for (auto& kv : ctx->free_blocks) cudaFreeAsync(kv.second, ctx->stream);
+    for (auto& kv : ctx->free_blocks) {
+        cudaFreeAsync(kv.second, ctx->stream);
+        ctx->pool_taken -= std::min(ctx->pool_taken, kv.first);
+    }
     ctx->free_blocks.clear();
     ctx->cached_bytes = 0;
     cudaStreamSynchronize(ctx->stream);
@@ -100,7 +105,10 @@ int pem_ctx_create(pem_ctx** out, int device)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit = total_b / 5 * 4;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        ctx->cache_limit = total_b / 5 * 4;
+        ctx->free_at_create = free_b;
+    }
     *out = ctx;
     return PEM_OK;
 }

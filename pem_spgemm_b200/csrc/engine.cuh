@@ -39,6 +39,8 @@ struct pem_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live_blocks;
     size_t cached_bytes = 0, cache_limit = (size_t)32 << 30;
+    size_t pool_taken = 0;       // bytes this context holds from its pool (live + cached)
+    size_t free_at_create = 0;   // device memory free when the context was created (cudaMemGetInfo costs ~1 ms: never on the hot path)
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int fail_cuda(cudaError_t e, const char* what, const char* file, int line)

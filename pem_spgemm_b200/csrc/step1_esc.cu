@@ -40,9 +40,24 @@
 #include <climits>
 #include <cstdlib>
 
+#include <chrono>
+
 #include "engine.cuh"
 
 namespace {
+
+// PEM_TRACE=1: host-side timeline of step 1 (where the host waits), printed to stderr
+struct Trace {
+    bool on;
+    std::chrono::high_resolution_clock::time_point t0;
+    Trace() : on(getenv("PEM_TRACE") != nullptr), t0(std::chrono::high_resolution_clock::now()) {}
+    void mark(const char* what)
+    {
+        if (!on) return;
+        auto t = std::chrono::high_resolution_clock::now();
+        fprintf(stderr, "[step1 %8.3f ms] %s\n", std::chrono::duration<double, std::milli>(t - t0).count(), what);
+    }
+};
 
 constexpr int EX_THREADS = 256;
 constexpr int EX_ITEMS = 8;                       // products per lane
@@ -356,6 +371,8 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     const int64_t nchunks64 = (total + EX_CHUNK - 1) / EX_CHUNK;
     if (nchunks64 > 0x7ffffff0LL) return ctx->fail(PEM_ERR_LIMIT, "step 1: more than 2^42 tile products");
     const int nchunks = (int)nchunks64;
+    Trace tr;
+    tr.mark("esc_run begin");
     int32_t* split = nullptr;
     int64_t* chunk_off = nullptr;
     KeyT *key_a = nullptr, *key_b = nullptr;
@@ -376,17 +393,20 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
 
     // Staged layout (one expansion): chunks write at their product base into P-sized buffers, then
     // the holes are closed.  When P-sized buffers would be too large, count first and write exactly.
-    size_t free_b = 0, total_b = 0;
-    E_CK(cudaMemGetInfo(&free_b, &total_b));
+    // free device memory, from the context's own books (cudaMemGetInfo takes ~0.7 ms on a B200 box)
+    const size_t free_b = ctx->free_at_create > ctx->pool_taken ? ctx->free_at_create - ctx->pool_taken : 0;
     const size_t staged_bytes = (size_t)P * (sizeof(KeyT) + sizeof(int2));
     // (PEM_ESC_TWO_PASS=1 forces the count-then-write variant; tests use it, nothing else should)
     const char* force2 = getenv("PEM_ESC_TWO_PASS");
-    const bool staged = !(force2 && *force2 == '1') &&
-                        staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
+    bool staged = !(force2 && *force2 == '1') &&
+                  staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
     int64_t F = 0;
+    if (staged && (pem_alloc(ctx, &key_b, (size_t)P) != PEM_OK || pem_alloc(ctx, &val_b, (size_t)P) != PEM_OK)) {
+        pem_free(ctx, key_b);              // the books were too optimistic (another process on the GPU?): count first
+        pem_free(ctx, val_b);
+        staged = false;
+    }
     if (staged) {
-        E_TRY(pem_alloc(ctx, &key_b, (size_t)P));
-        E_TRY(pem_alloc(ctx, &val_b, (size_t)P));
         KT_BEGIN(KT_EXPAND);
         k_expand<KeyT, 1, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
             np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
@@ -404,6 +424,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     E_CK(cudaMemcpyAsync(ctx->h_scalars, chunk_off + nchunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
     E_CK(cudaStreamSynchronize(ctx->stream));
     F = ctx->h_scalars[0];
+    tr.mark("expand done, F known");
     C->pairs = F;
     if (F == 0) {
         cleanup();
@@ -456,6 +477,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         E_CK(cudaStreamSynchronize(ctx->stream));
     }
     const int64_t T = ctx->h_scalars[0];
+    tr.mark("sort+select done, T known");
     C->tiles = T;
     pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col); pem_free(ctx, C->pair_ptr);
     E_TRY(pem_alloc(ctx, &C->tile_row, (size_t)T));
@@ -469,6 +491,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     C->pair_list = val_a;
     val_a = nullptr;
     cleanup();
+    tr.mark("esc_run end (k_ctiles launched)");
 #undef E_TRY
 #undef E_CK
 #undef E_LAUNCHED

@@ -316,3 +316,41 @@ def test_esc_count_then_write_variant(engine, k):
         for a, b in zip(ref, arrs):
             assert np.array_equal(a, b), key
     A.free()
+
+
+def test_config2_full_size_matches_oracle(engine):
+    """BASELINE config 2 at full size (3.09 M nonzeros, nnz(C) = 67.7 M): structure and values of C
+    against the host oracle, bit for bit."""
+    name, tb, (rows, cols, I, J, V) = synth.config(2)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    C = engine.spgemm(A, A)
+    oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, False)
+    assert engine.count_flop(A, A) == host.flop(oA, oB) == 92_217_721
+    assert C.info.nnz == oC.nnz == 67_736_942
+    _assert_same_C(C, oC)
+    C.free(); A.free()
+
+
+def test_config4_full_size_known_answers_and_checksum(engine):
+    """BASELINE config 4 at full size against the analytic figures pinned in SURVEY.md section 8c and a
+    size-independent property: sum(C) = sum_k colsum_k(A) * rowsum_k(A)."""
+    name, tb, (rows, cols, I, J, V) = synth.config(4)
+    assert (rows, I.size) == (5_147_788, 96_915_634)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    assert A.info.tiles == 5_418_031
+    assert engine.count_flop(A, A) == 1_828_978_714
+    engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 1)          # the reference's C' (structurally reachable tiles)
+    try:
+        C = engine.step1(A, A)
+        assert (C.info.tiles, C.info.pairs) == (23_814_841, 91_431_915)
+        C.free()
+    finally:
+        engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+    C = engine.spgemm(A, A)
+    assert C.info.nnz == 470_380_286
+    s, a = C.checksum()
+    rowsum = np.bincount(I, weights=V, minlength=rows)
+    colsum = np.bincount(J, weights=V, minlength=cols)
+    want = float(np.dot(colsum, rowsum))
+    assert abs(s - want) <= 1e-9 * abs(want) and abs(a - want) <= 1e-9 * abs(want)   # all values positive
+    C.free(); A.free()

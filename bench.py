@@ -312,8 +312,14 @@ def main():
     for _ in range(max(3, min(args.steps, 5))):
         barrier()
         t0 = time.perf_counter()
-        A2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
-        B2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A2
+        if world > 1:       # each rank uploads 1/world of the COO, NVLink all-gather, conversion from device arrays
+            dI, dJ, dV, h2d_rank = pdist.upload_coo_sharded(tI, tJ, tV, torch.device("cuda", local_rank))
+            torch.cuda.current_stream().synchronize()
+            A2 = ctx.convert_coo(rows, cols, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), nnz=I.size)
+            B2 = ctx.convert_coo(rows, cols, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), nnz=I.size, transpose=True) if tb else A2
+        else:
+            A2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
+            B2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A2
         chk = [0.0, 0.0]
         for pn in panels:
             C2 = ctx.spgemm(A2, B2, panel=pn)
@@ -329,7 +335,7 @@ def main():
             B2.free()
         A2.free()
     e2e_t = float(np.mean(e2e_ms[1:])) if len(e2e_ms) > 1 else e2e_ms[0]
-    h2d = int(I.nbytes + J.nbytes + V.nbytes) * (2 if tb else 1)
+    h2d = int(I.nbytes + J.nbytes + V.nbytes) * (2 if tb else 1) if world == 1 else int(h2d_rank) * world
     d2h = (2 * 1024 * 2 * 8 + 3 * 8 * 16) * sub     # checksum partials + the size read-backs of one step
 
     if rank == 0:
@@ -369,7 +375,8 @@ def main():
                          "whole_spgemm_frac": bytes_alg / (ms_per_step * 1e6) / peak},
             "e2e": {"value": 2.0 * flop / (e2e_t * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_t,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "host COO (pinned) -> pem_convert_coo -> pem_spgemm -> checksum/sizes read back"},
+                    "what": "host COO (pinned) -> pem_convert_coo -> pem_spgemm -> checksum/sizes read back"
+                            + ("; every rank uploads 1/N of the COO and the slices are all-gathered over NVLink" if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -63,3 +63,29 @@ def split_by_weight(weights: np.ndarray, nparts: int) -> np.ndarray:
         # first r with run[r] * nparts >= total * p
         bounds[p] = min(int(np.searchsorted(run * nparts, total * p, side="left")) + 1, w.size)
     return np.maximum.accumulate(bounds)
+
+
+def upload_coo_sharded(I, J, V, device):
+    """Multi-GPU ingest of one host COO: every rank uploads only its 1/world slice over its own PCIe
+    link (pinned host -> device) and the slices are all-gathered over NVLink, so each GPU ends up with
+    the full COO (B is replicated, A's panel is cut later by tile row) after 1/world of the host->device
+    traffic.  I/J/V are pinned torch tensors holding the FULL arrays on every rank.  Returns device
+    tensors (I, J, V) of the full length and the number of bytes this rank copied from the host."""
+    import torch
+    import torch.distributed as dist
+    n = I.numel()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        out = [t.to(device, non_blocking=True) for t in (I, J, V)]
+        return out[0], out[1], out[2], sum(t.numel() * t.element_size() for t in (I, J, V))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = -(-n // world)
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    full, copied = [], 0
+    for t in (I, J, V):
+        g = torch.empty(world * per, dtype=t.dtype, device=device)
+        mine = g[rank * per: (rank + 1) * per]          # all_gather in place: own slice lives inside the output
+        mine[: hi - lo].copy_(t[lo:hi], non_blocking=True)
+        copied += (hi - lo) * t.element_size()
+        dist.all_gather_into_tensor(g, mine)
+        full.append(g[:n])                               # only the last slice is padded, and the padding is the tail
+    return full[0], full[1], full[2], copied

@@ -247,7 +247,7 @@ def main():
     # operands resident in HBM before the timed region
     tI = torch.from_numpy(I).pin_memory(); tJ = torch.from_numpy(J).pin_memory(); tV = torch.from_numpy(V).pin_memory()
     A = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
-    B = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A
+    B = ctx.transpose(A) if tb else A
     flop = ctx.count_flop(A, B)
     sub = args.subpanels or (max(1, -(-8 // world)) if args.config == 5 else 1)
     bounds = ctx.partition_panels(A, B, world * sub)
@@ -316,10 +316,10 @@ def main():
             dI, dJ, dV, h2d_rank = pdist.upload_coo_sharded(tI, tJ, tV, torch.device("cuda", local_rank))
             torch.cuda.current_stream().synchronize()
             A2 = ctx.convert_coo(rows, cols, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), nnz=I.size)
-            B2 = ctx.convert_coo(rows, cols, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), nnz=I.size, transpose=True) if tb else A2
+            B2 = ctx.transpose(A2) if tb else A2
         else:
             A2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
-            B2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy(), transpose=True) if tb else A2
+            B2 = ctx.transpose(A2) if tb else A2        # A^T from A's tiles, on the device
         chk = [0.0, 0.0]
         for pn in panels:
             C2 = ctx.spgemm(A2, B2, panel=pn)
@@ -335,7 +335,7 @@ def main():
             B2.free()
         A2.free()
     e2e_t = float(np.mean(e2e_ms[1:])) if len(e2e_ms) > 1 else e2e_ms[0]
-    h2d = int(I.nbytes + J.nbytes + V.nbytes) * (2 if tb else 1) if world == 1 else int(h2d_rank) * world
+    h2d = int(I.nbytes + J.nbytes + V.nbytes) if world == 1 else int(h2d_rank) * world
     d2h = (2 * 1024 * 2 * 8 + 3 * 8 * 16) * sub     # checksum partials + the size read-backs of one step
 
     if rank == 0:

@@ -121,6 +121,11 @@ int64_t pem_ctx_pool_bytes(const pem_ctx* ctx);
 int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
                     const int32_t* I, const int32_t* J, const double* V, int transpose,
                     pem_tiled** out, pem_times* times);
+/* The transpose of a tiled matrix, built on the device from A's tiles (tile keys re-sorted, masks and
+ * column masks swap roles, values moved to their column-major slots): B = A^T for the CLI's
+ * `[1]` mode without parsing, uploading and sorting the COO a second time (the reference converts
+ * the file twice, spgemm.cu:778-792, 849-978).  Bit-identical to pem_convert_coo(..., transpose=1). */
+int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out);
 int pem_tiled_info_get(const pem_tiled* t, pem_tiled_info* info);
 void pem_tiled_free(pem_ctx* ctx, pem_tiled* t);
 

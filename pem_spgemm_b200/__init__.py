@@ -69,7 +69,8 @@ class ResultInfo(C.Structure):
 
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
-    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_kernel_ms", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_info_get",
+    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_kernel_ms", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
+    "pem_tiled_info_get",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
     "pem_result_info_get", "pem_result_free", "pem_result_get", "pem_result_device_ptr",
@@ -107,6 +108,7 @@ def load():
         "pem_ctx_pool_bytes": (i64, [vp]),
         "pem_ctx_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
         "pem_convert_coo": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
+        "pem_tiled_transpose": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pem_tiled_info_get": (C.c_int, [vp, C.POINTER(TiledInfo)]),
         "pem_tiled_free": (None, [vp, vp]),
         "pem_tiled_get": (C.c_int, [vp, vp, C.c_int, vp, C.c_size_t]),
@@ -212,6 +214,12 @@ class Context:
                                     C.byref(h), C.byref(times) if times is not None else None)
         self._keep = None
         self._check(rc)
+        return Tiled(self, h)
+
+    def transpose(self, A: "Tiled") -> "Tiled":
+        """A^T from A's tiles, on the device."""
+        h = C.c_void_p()
+        self._check(load().pem_tiled_transpose(self._h, A._h, C.byref(h)))
         return Tiled(self, h)
 
     def count_flop(self, A: "Tiled", B: "Tiled") -> int:

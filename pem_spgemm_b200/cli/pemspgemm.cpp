@@ -13,7 +13,8 @@
 // Environment (the positional surface is unchanged): PEM_REPEAT (default 10, Makefile:34),
 // PEM_WARMUP (default 1, spgemm.cu:712-714), PEM_DEVICE (default 0), PEM_DUMP_DIR (default /tmp),
 // PEM_CSV (default ./pemspgemm_benchmark_result.csv), PEM_KEEP_EMPTY=1 for reference-faithful
-// "C tiles" (PEM_OPT_KEEP_EMPTY_TILES).
+// "C tiles" (PEM_OPT_KEEP_EMPTY_TILES), PEM_PANELS=n to multiply in n sequential tile-row panels (a C that does not
+// fit the GPU in tiled form is produced, dumped and freed panel by panel; timings are summed over the panels).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -86,8 +87,9 @@ int main(int argc, char* argv[])
     rc = pem_convert_coo(ctx, rows, cols, nnz, I, J, V, 0, &A, &ta);
     DIE_IF(rc, ctx, "conversion of A");
     if (aat) {
-        rc = pem_convert_coo(ctx, rows, cols, nnz, I, J, V, 1, &B, &tb);
+        rc = pem_tiled_transpose(ctx, A, &B);          // B = A^T from A's tiles: no second parse / upload / sort
         DIE_IF(rc, ctx, "conversion of B");
+        tb.convert_kernel_ms = ta.convert_kernel_ms;
     } else {
         B = A;  // A^2: one conversion serves both operands
     }
@@ -105,16 +107,27 @@ int main(int argc, char* argv[])
     std::cout << "\nstep1 tile-level symbolic (bitmap / hash accumulators), B tile columns: " << ib.tile_cols << "\n";
     std::cout << "\nstep2 pemSpGEMM\n" << "\nstep3 pemSpGEMM\n\n\n";
 
-    pem_result* C = nullptr;
+    const int PANELS = std::max(1, env_int("PEM_PANELS", 1));
+    std::vector<int32_t> bounds((size_t)PANELS + 1);
+    rc = pem_partition_panels(ctx, A, B, PANELS, bounds.data());
+    DIE_IF(rc, ctx, "panel split");
+    pem_result* C = nullptr;                      // the last panel of the last iteration (the whole C when PANELS == 1)
+    int64_t c_tiles = 0, c_nnz = 0;
     double s1 = 0, s2 = 0, s3 = 0, total = 0, kernel = 0, mall = 0;
     for (int n = 0; n < WARMUP + REPEAT; ++n) {
-        if (C) { pem_result_free(ctx, C); C = nullptr; }
-        pem_times t = {};
-        rc = pem_spgemm(ctx, A, B, &C, &t);
-        DIE_IF(rc, ctx, "spgemm");
-        if (n >= WARMUP) {
-            s1 += t.step1_ms; s2 += t.step2_ms; s3 += t.step3_ms;
-            total += t.total_ms; kernel += t.kernel_ms; mall += t.malloc_ms;
+        c_tiles = c_nnz = 0;
+        for (int pn = 0; pn < PANELS; ++pn) {
+            if (C) { pem_result_free(ctx, C); C = nullptr; }
+            pem_times t = {};
+            rc = pem_spgemm_panel(ctx, A, B, bounds[(size_t)pn], bounds[(size_t)pn + 1], &C, &t);
+            DIE_IF(rc, ctx, "spgemm");
+            pem_result_info pi;
+            pem_result_info_get(C, &pi);
+            c_tiles += pi.tiles; c_nnz += pi.nnz;
+            if (n >= WARMUP) {
+                s1 += t.step1_ms; s2 += t.step2_ms; s3 += t.step3_ms;
+                total += t.total_ms; kernel += t.kernel_ms; mall += t.malloc_ms;
+            }
         }
     }
     s1 /= REPEAT; s2 /= REPEAT; s3 /= REPEAT; total /= REPEAT; kernel /= REPEAT; mall /= REPEAT;
@@ -122,6 +135,7 @@ int main(int argc, char* argv[])
 
     pem_result_info ic;
     pem_result_info_get(C, &ic);
+    ic.tiles = c_tiles; ic.nnz = c_nnz;           // totals over the panels
     const double gflops = flop * 2.0 / (total * 1e6);                 // spgemm.cu:1403
     const double compression = ic.nnz ? (double)flop / (double)ic.nnz : 0.0;  // spgemm.cu:1404
 
@@ -161,26 +175,31 @@ int main(int argc, char* argv[])
     } else {
         const char* dd = getenv("PEM_DUMP_DIR");
         std::string dir = dd && *dd ? dd : "/tmp";
-        std::vector<int32_t> r((size_t)ic.nnz), c((size_t)ic.nnz);
-        std::vector<double> v((size_t)ic.nnz);
-        rc = pem_result_to_coo(ctx, C, r.data(), c.data(), v.data());
-        DIE_IF(rc, ctx, "COO export");
         std::cout << "Saving results to " << dir << "/SPGEMM_RESULT_*.txt\n";
         std::ofstream out;
         out.open(dir + "/SPGEMM_RESULT_NNZ.txt");
         out << ic.nnz;                                   // no trailing newline (spgemm.cu:1546)
         out.close();
-        out.open(dir + "/SPGEMM_RESULT_ROWS.txt");
-        for (auto x : r) out << x << "\n";
-        out.close();
-        out.open(dir + "/SPGEMM_RESULT_COLS.txt");
-        for (auto x : c) out << x << "\n";
-        out.close();
-        out.open(dir + "/SPGEMM_RESULT_VALS.txt");
-        out << std::fixed << std::setprecision(std::numeric_limits<double>::max_digits10);
-        for (auto x : v) out << x << "\n";
-        out.close();
-        if (!out) exit_code = 2;
+        std::ofstream fr(dir + "/SPGEMM_RESULT_ROWS.txt"), fc(dir + "/SPGEMM_RESULT_COLS.txt"), fv(dir + "/SPGEMM_RESULT_VALS.txt");
+        fv << std::fixed << std::setprecision(std::numeric_limits<double>::max_digits10);
+        for (int pn = 0; pn < PANELS; ++pn) {            // panels in order = rows in order
+            if (PANELS > 1) {                             // only the last panel is still alive: recompute the others
+                pem_result_free(ctx, C); C = nullptr;
+                rc = pem_spgemm_panel(ctx, A, B, bounds[(size_t)pn], bounds[(size_t)pn + 1], &C, nullptr);
+                DIE_IF(rc, ctx, "spgemm");
+            }
+            pem_result_info pi;
+            pem_result_info_get(C, &pi);
+            std::vector<int32_t> r((size_t)pi.nnz), c((size_t)pi.nnz);
+            std::vector<double> v((size_t)pi.nnz);
+            rc = pem_result_to_coo(ctx, C, r.data(), c.data(), v.data());
+            DIE_IF(rc, ctx, "COO export");
+            for (auto x : r) fr << x << "\n";
+            for (auto x : c) fc << x << "\n";
+            for (auto x : v) fv << x << "\n";
+        }
+        fr.close(); fc.close(); fv.close();
+        if (!fr || !fc || !fv) exit_code = 2;
     }
     std::cout << "CLEANING UP RESOURCES\n\n";
     pem_result_free(ctx, C);

@@ -300,6 +300,86 @@ k_tile_prodcost(const uint16_t* __restrict__ col_occ, const int32_t* __restrict_
     if (ps) atomicAdd(&row_sliced_cost[tile_row[t]], ps);
 }
 
+// ---- transpose of a tiled matrix on the device ----------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_transpose_keys(const int32_t* __restrict__ tile_row, const int32_t* __restrict__ tile_col, int cnt, int rbits,
+                 uint64_t* __restrict__ keys, int32_t* __restrict__ ids)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    keys[t] = ((uint64_t)(unsigned)tile_col[t] << rbits) | (uint64_t)(unsigned)tile_row[t];   // new (row, col)
+    ids[t] = t;
+}
+
+__global__ void __launch_bounds__(256)
+k_transpose_counts(const int32_t* __restrict__ perm, const uint32_t* __restrict__ nnz_ptr, int cnt, int64_t* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > cnt) return;
+    out[t] = t < cnt ? (int64_t)(nnz_ptr[perm[t] + 1] - nnz_ptr[perm[t]]) : 0;
+}
+
+// thread per tile of the transpose: masks swap roles, values move to their column-major position
+__global__ void __launch_bounds__(128)
+k_transpose_tiles(int cnt, int tile_rows_new, const int32_t* __restrict__ perm, const int64_t* __restrict__ new_ptr,
+                  const uint32_t* __restrict__ o_nnz_ptr, const uint16_t* __restrict__ o_masks,
+                  const uint16_t* __restrict__ o_masks_t, const int32_t* __restrict__ o_row, const int32_t* __restrict__ o_col,
+                  const uint16_t* __restrict__ o_col_occ, const uint16_t* __restrict__ o_row_occ,
+                  const uint8_t* __restrict__ o_rc, const double* __restrict__ o_vals,
+                  uint32_t* __restrict__ n_nnz_ptr, uint16_t* __restrict__ n_masks, uint16_t* __restrict__ n_masks_t,
+                  uint8_t* __restrict__ n_row_ptr, int32_t* __restrict__ n_row, int32_t* __restrict__ n_col,
+                  int32_t* __restrict__ n_tile_row_ptr, uint16_t* __restrict__ n_col_occ, uint16_t* __restrict__ n_row_occ,
+                  uint8_t* __restrict__ n_rc, double* __restrict__ n_vals)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const int o = perm[t];
+    const uint4* mt4 = reinterpret_cast<const uint4*>(o_masks_t + (size_t)o * 16);     // new row masks
+    const uint4 a = mt4[0], b = mt4[1];
+    const uint4* m4 = reinterpret_cast<const uint4*>(o_masks + (size_t)o * 16);        // new column masks
+    reinterpret_cast<uint4*>(n_masks + (size_t)t * 16)[0] = a;
+    reinterpret_cast<uint4*>(n_masks + (size_t)t * 16)[1] = b;
+    reinterpret_cast<uint4*>(n_masks_t + (size_t)t * 16)[0] = m4[0];
+    reinterpret_cast<uint4*>(n_masks_t + (size_t)t * 16)[1] = m4[1];
+    const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    unsigned rp[16], packed[4] = {0, 0, 0, 0};
+    unsigned run = 0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        rp[r] = run;
+        packed[r >> 2] |= run << (8 * (r & 3));
+        run += __popc((w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu);
+    }
+    *reinterpret_cast<uint4*>(n_row_ptr + (size_t)t * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    const int nr = o_col[o], nc = o_row[o];
+    n_row[t] = nr;
+    n_col[t] = nc;
+    n_col_occ[t] = o_row_occ[o];
+    n_row_occ[t] = o_col_occ[o];
+    const uint32_t ns = (uint32_t)new_ptr[t];
+    n_nnz_ptr[t] = ns;
+    const int prev = t ? o_col[perm[t - 1]] : -1;
+    for (int r = prev + 1; r <= nr; ++r) n_tile_row_ptr[r] = t;
+    if (t == cnt - 1) {
+        for (int r = nr + 1; r <= tile_rows_new; ++r) n_tile_row_ptr[r] = cnt;
+        n_nnz_ptr[cnt] = (uint32_t)new_ptr[cnt];
+    }
+    const uint32_t s = o_nnz_ptr[o], e = o_nnz_ptr[o + 1];
+    for (uint32_t x = s; x < e; ++x) {
+        const unsigned rc = o_rc[x];
+        const unsigned r = rc >> 4, c = rc & 15u;          // old (r, c) -> new (c, r)
+        unsigned first = 0, m = 0;                          // rp[c], new row mask c (dynamic c: selects)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            first = c == (unsigned)j ? rp[j] : first;
+            m = c == (unsigned)j ? ((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) : m;
+        }
+        const uint32_t at = ns + first + __popc(m & ((1u << r) - 1u));
+        n_vals[at] = o_vals[x];
+        n_rc[at] = (uint8_t)((c << 4) | r);
+    }
+}
+
 bool is_device_ptr(const void* p)
 {
     cudaPointerAttributes at;
@@ -528,6 +608,67 @@ int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* Tc, bool as_a, bool as_
 }
 
 extern "C" {
+
+int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
+{
+    if (!ctx || !A || !out) return PEM_ERR_ARG;
+    *out = nullptr;
+    PEM_CK(cudaSetDevice(ctx->device));
+    pem_tiled* T = new pem_tiled();
+    T->rows = A->cols; T->cols = A->rows; T->nnz = A->nnz;
+    T->tile_rows = A->tile_cols; T->tile_cols = A->tile_rows; T->tiles = A->tiles;
+    const size_t n = (size_t)A->tiles;
+    uint64_t *keys = nullptr, *keys2 = nullptr;
+    int32_t *ids = nullptr, *perm = nullptr;
+    int64_t* nptr = nullptr;
+    char* tmp = nullptr;
+    auto fail = [&](int rc) {
+        pem_free(ctx, keys); pem_free(ctx, keys2); pem_free(ctx, ids); pem_free(ctx, perm); pem_free(ctx, nptr); pem_free(ctx, tmp);
+        pem_tiled_free(ctx, T);
+        return rc;
+    };
+#define TR_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) return fail(rc_); } while (0)
+#define TR_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx->fail_cuda(e_, #call, __FILE__, __LINE__)); } while (0)
+    TR_TRY(pem_alloc(ctx, &T->tile_row_ptr, (size_t)T->tile_rows + 1));
+    TR_CK(cudaMemsetAsync(T->tile_row_ptr, 0, ((size_t)T->tile_rows + 1) * 4, ctx->stream));
+    TR_TRY(pem_alloc(ctx, &T->vals, (size_t)T->nnz)); TR_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)T->nnz));
+    TR_TRY(pem_alloc(ctx, &T->tile_nnz_ptr, n + 1)); TR_TRY(pem_alloc(ctx, &T->masks, n * 16));
+    TR_TRY(pem_alloc(ctx, &T->masks_t, n * 16)); TR_TRY(pem_alloc(ctx, &T->row_ptr, n * 16));
+    TR_TRY(pem_alloc(ctx, &T->tile_col_idx, n)); TR_TRY(pem_alloc(ctx, &T->tile_row_idx, n));
+    TR_TRY(pem_alloc(ctx, &T->col_occ, n)); TR_TRY(pem_alloc(ctx, &T->row_occ, n));
+    if (n == 0) {
+        TR_CK(cudaMemsetAsync(T->tile_nnz_ptr, 0, 4, ctx->stream));
+        *out = T;
+        return PEM_OK;
+    }
+    const int rbits = h_bits_for(A->tile_rows), cbits = h_bits_for(A->tile_cols);
+    TR_TRY(pem_alloc(ctx, &keys, n)); TR_TRY(pem_alloc(ctx, &keys2, n));
+    TR_TRY(pem_alloc(ctx, &ids, n)); TR_TRY(pem_alloc(ctx, &perm, n));
+    TR_TRY(pem_alloc(ctx, &nptr, n + 1));
+    k_transpose_keys<<<pem_div_up((int64_t)n, 256), 256, 0, ctx->stream>>>(A->tile_row_idx, A->tile_col_idx, (int)n, rbits, keys, ids);
+    ++ctx->launches;
+    TR_CK(cudaGetLastError());
+    size_t tb = 0;
+    TR_CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, ids, perm, (int64_t)n, 0, rbits + cbits, ctx->stream));
+    TR_TRY(pem_alloc(ctx, &tmp, tb));
+    TR_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, ids, perm, (int64_t)n, 0, rbits + cbits, ctx->stream));
+    ctx->launches += 2 + (rbits + cbits + 7) / 8;
+    k_transpose_counts<<<pem_div_up((int64_t)n + 1, 256), 256, 0, ctx->stream>>>(perm, A->tile_nnz_ptr, (int)n, nptr);
+    ++ctx->launches;
+    TR_CK(cudaGetLastError());
+    TR_TRY(pem_scan_exclusive_i64(ctx, nptr, (int64_t)n + 1));
+    k_transpose_tiles<<<pem_div_up((int64_t)n, 128), 128, 0, ctx->stream>>>(
+        (int)n, T->tile_rows, perm, nptr, A->tile_nnz_ptr, A->masks, A->masks_t, A->tile_row_idx, A->tile_col_idx, A->col_occ,
+        A->row_occ, A->rc_idx, A->vals, T->tile_nnz_ptr, T->masks, T->masks_t, T->row_ptr, T->tile_row_idx, T->tile_col_idx,
+        T->tile_row_ptr, T->col_occ, T->row_occ, T->rc_idx, T->vals);
+    ++ctx->launches;
+    TR_CK(cudaGetLastError());
+#undef TR_TRY
+#undef TR_CK
+    pem_free(ctx, keys); pem_free(ctx, keys2); pem_free(ctx, ids); pem_free(ctx, perm); pem_free(ctx, nptr); pem_free(ctx, tmp);
+    *out = T;
+    return PEM_OK;
+}
 
 int pem_count_flop(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, uint64_t* flop)
 {

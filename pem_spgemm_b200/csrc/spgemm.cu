@@ -587,6 +587,8 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
 {
     if (!ctx || !A || !B || !C) return PEM_ERR_ARG;
     if (C->stage != 1) return ctx->fail(PEM_ERR_ARG, "step 2 needs a result fresh from step 1");
+    if (C->tiles >= 0x7fffffffLL)
+        return ctx->fail(PEM_ERR_LIMIT, "more than 2^31 C' tiles in one result: multiply in tile-row panels (pem_spgemm_panel)");
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_alloc(ctx, &C->masks, (size_t)C->tiles * 16));
     PEM_TRY(pem_alloc(ctx, &C->tile_nnz_ptr, (size_t)C->tiles + 1));

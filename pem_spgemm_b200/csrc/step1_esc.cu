@@ -477,6 +477,10 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         E_CK(cudaStreamSynchronize(ctx->stream));
     }
     const int64_t T = ctx->h_scalars[0];
+    if (T >= 0x7fffffffLL) {
+        cleanup();
+        return ctx->fail(PEM_ERR_LIMIT, "more than 2^31 C' tiles in one result: multiply in tile-row panels (pem_spgemm_panel)");
+    }
     tr.mark("sort+select done, T known");
     C->tiles = T;
     pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col); pem_free(ctx, C->pair_ptr);

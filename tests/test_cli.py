@@ -67,6 +67,14 @@ def test_cli_report_csv_and_dump(tmp_path, aat):
     assert len(f) == 14 and f[0] == "case_a" and int(f[1]) == flop and int(f[2]) == ro.size
     assert f[3] == f"{flop / ro.size:.2f}"
     assert all(len(x.split(".")[1]) == 2 for x in f[3:])
+    # the same product in 3 sequential tile-row panels: identical dump
+    env3 = dict(env, PEM_PANELS="3", PEM_DUMP_DIR=str(tmp_path / "p3"), PEM_CSV=str(tmp_path / "p3.csv"))
+    os.makedirs(tmp_path / "p3")
+    out = _run([mtx, "1"] + (["1"] if aat else []), tmp_path, env3)
+    assert out.returncode == 0, out.stderr
+    assert f"C nnz: {ro.size}" in out.stdout
+    for name in ("NNZ", "ROWS", "COLS", "VALS"):
+        assert open(tmp_path / "p3" / f"SPGEMM_RESULT_{name}.txt").read() == open(tmp_path / f"SPGEMM_RESULT_{name}.txt").read()
     out = _run([mtx, "0"] + (["1"] if aat else []), tmp_path, env)      # second run appends
     assert out.returncode == 0 and "Not saving results. Exiting." in out.stdout
     assert open(tmp_path / "pemspgemm_benchmark_result.csv").read().count("\n") == 2

@@ -72,6 +72,21 @@ def test_dense_blocks_all_step3_variants(engine):
         A.free()
 
 
+@pytest.mark.parametrize("shape,nnz,seed", SHAPES + [((16, 16), 0, 9)])
+def test_device_transpose_equals_transposed_conversion(engine, shape, nnz, seed):
+    """pem_tiled_transpose (A^T from A's tiles) must reproduce pem_convert_coo(transpose=1) array by array."""
+    rows, cols, I, J, V = synth.random_sparse(*shape, nnz, seed=seed)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    T = engine.transpose(A)
+    _check_tiled(T, tiles.tile_format(rows, cols, I, J, V, transpose=True))
+    if I.size:
+        C = engine.spgemm(A, T)
+        _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, True)
+        _assert_same_C(C, oC)
+        C.free()
+    T.free(); A.free()
+
+
 def test_conversion_dense_tile_and_empty(engine):
     I, J = np.divmod(np.arange(256, dtype=np.int32), 16)
     V = np.arange(256, dtype=np.float64)

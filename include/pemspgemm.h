@@ -59,10 +59,11 @@ typedef enum pem_option {
      * SPA and NSPARSE hashing `B_tileCols > 512*32` (spgemm.cu:1142). */
     PEM_OPT_STEP1_PATH = 2,
     /* thread mapping of step 3 (and of step 2 for value 1).  Results are bit-identical.
-     * 0 (default) = automatic (currently always entry-owner: it measured fastest on all workloads)
+     * 0 (default) = automatic (currently always 2: it measured fastest on every workload, profiles/r01_summary.md)
      * 1 = row-owner: sixteen lanes per C' tile, lane = tile row (steps 2 and 3)
      * 2 = entry-owner: one thread per C nonzero (dense lane packing; hypersparse tiles)
-     * 3 = tile-owner: one warp per C' tile, lane = nonzero, pair data shared through shuffles */
+     * 3 = tile-owner: one warp per C' tile, lane = nonzero, pair data shared through shuffles
+     * 4 = row-owner with a dense 16x16 shared-memory accumulator per tile (dense tiles: stencils, FEM) */
     PEM_OPT_OWNER = 3
 } pem_option;
 

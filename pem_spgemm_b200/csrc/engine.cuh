@@ -25,7 +25,7 @@ struct pem_ctx {
     int64_t launches = 0;        // kernels of this library launched on the stream
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
-    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = auto, 1 = row-owner, 2 = entry-owner, 3 = tile-owner
+    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = auto, 1 = row-owner (registers), 2 = entry-owner, 3 = tile-owner, 4 = row-owner (shared-memory accumulator)
     int sm_count = 148;
     int smem_optin = 227 * 1024; // max dynamic shared memory per block
     int64_t* h_scalars = nullptr; // pinned, PEM_NSCALARS entries: size read-backs
@@ -134,7 +134,8 @@ struct pem_result {
     int32_t tile_cols = 0;
     int64_t tiles = 0, pairs = 0, nnz = 0, tile_products = 0;
     int stage = 0;                    // 1, 2, 3 = last completed step
-    bool s3_tiles = false;            // step 3 runs a warp per C' tile (dense tiles) instead of a thread per nonzero
+    bool s3_tiles = false;            // step 3 runs a warp per C' tile instead of a thread per nonzero
+    bool s3_rows = false;             // step 3 runs sixteen lanes per C' tile with a dense shared-memory accumulator
     int64_t* row_ptr = nullptr;       // [re-rb+1]
     int32_t* tile_row = nullptr;      // [tiles]
     int32_t* tile_col = nullptr;      // [tiles]

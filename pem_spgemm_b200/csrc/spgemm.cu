@@ -566,6 +566,85 @@ k_step3_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2*
     }
 }
 
+// step 3 (row-owner, dense accumulator): SIXTEEN LANES PER C' TILE, lane = tile row r, with the row's 16
+// possible entries accumulated in shared memory.  The lane runs Gustavson inside the tile pair:
+//     for k in Arow[r] (ascending; the row's values are consecutive):  a = *ap++
+//         for c in Brow[k] (ascending; consecutive values):            acc[r][c] = fma(a, *bp++, acc[r][c])
+// so it only ever touches products that exist - no per-entry "does this pair feed me" test - and
+// every product lands on a structural nonzero of C by construction of the mask.  Each C entry still
+// receives its products in ascending (pair, k), i.e. the oracle's order: same bits as every other
+// variant.  Rows are padded to 17 doubles so the 16 lanes of a tile hit distinct banks unless their
+// r + c coincide.  Used when C's tiles are dense (stencil / FEM matrices: ~30 nonzeros per tile), where
+// the entry-owner kernel spends most of its instructions on (entry, pair) combinations without products.
+constexpr int S3R_THREADS = 256;
+__global__ void __launch_bounds__(S3R_THREADS)
+k_step3_rows(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+             const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
+             const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals, const uint32_t* __restrict__ A_row_rec,
+             const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals, const uint32_t* __restrict__ B_row_rec,
+             double* __restrict__ C_vals)
+{
+    __shared__ double s_acc[S3R_THREADS / 16][16 * 17];
+    const int tid = threadIdx.x;
+    const int64_t t = ((int64_t)blockIdx.x * S3R_THREADS + tid) >> 4;
+    const unsigned r = tid & 15u;
+    if (t >= n_tiles) return;                       // whole 16-lane groups leave together
+    const unsigned grp = 0xFFFFu << (tid & 16);
+    const unsigned cm = Cmasks[t * 16 + r];
+    const int pc = __popc(cm);
+    int incl = pc;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(grp, incl, o, 16);
+        if ((int)r >= o) incl += v;
+    }
+    if (cm == 0) return;                            // nothing lands in this row
+    double* __restrict__ acc = &s_acc[tid >> 4][r * 17];
+    {
+        unsigned z = cm;
+        while (z) {
+            acc[__ffs(z) - 1] = 0.0;
+            z &= z - 1;
+        }
+    }
+    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
+    int2 ab = pairs[ps];
+    unsigned ar = A_row_rec[(unsigned)ab.x * 16u + r];
+    for (int64_t i = ps; i < pe; ++i) {
+        const int2 cur = ab;
+        unsigned am = ar & 0xFFFFu;
+        const unsigned a_first = ar >> 16;
+        if (i + 1 < pe) {                           // next pair's ids and A row record while this one is consumed
+            ab = pairs[i + 1];
+            ar = A_row_rec[(unsigned)ab.x * 16u + r];
+        }
+        if (am) {
+            const double* __restrict__ ap = A_vals + (A_off[cur.x] + a_first);
+            const uint32_t* __restrict__ brec = B_row_rec + (size_t)(unsigned)cur.y * 16u;
+            const double* __restrict__ bvals = B_vals + B_off[cur.y];
+            do {
+                const unsigned k = __ffs(am) - 1;
+                am &= am - 1;
+                const double a = *ap++;
+                const unsigned br = brec[k];
+                unsigned bm = br & 0xFFFFu;
+                const double* __restrict__ bp = bvals + (br >> 16);
+                while (bm) {
+                    const unsigned c = __ffs(bm) - 1;
+                    bm &= bm - 1;
+                    acc[c] = fma(a, *bp++, acc[c]);
+                }
+            } while (am);
+        }
+    }
+    double* __restrict__ out = C_vals + c_tile_nnz_ptr[t] + (incl - pc);
+    unsigned m = cm;
+    while (m) {
+        *out++ = acc[__ffs(m) - 1];
+        m &= m - 1;
+    }
+}
+
 __global__ void k_set_last_i64(int64_t* p, int64_t idx, int64_t v) { p[idx] = v; }
 
 }  // namespace
@@ -642,7 +721,8 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     // (measured on B200, profiles/: the entry-owner kernel wins on every BASELINE config, including the
     // stencil matrix with ~30 nonzeros per C tile, so the tile-owner kernel is opt-in)
     C->s3_tiles = ctx->opt_owner == 3;
-    if (!rows_variant && !C->s3_tiles) {   // what the entry-owner step 3 reads: first tile of every 256-nonzero block
+    C->s3_rows = ctx->opt_owner == 4;     // measured 20.8 ms against 13.3 ms on config 4: opt-in as well
+    if (!rows_variant && !C->s3_tiles && !C->s3_rows) {   // what the entry-owner step 3 reads: first tile of every 256-nonzero block
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
         if (C->tiles > 0) {
@@ -659,8 +739,19 @@ int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_
     if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
+    if (C->nnz > 0 && C->s3_rows) {         // views are cached on the handles after the first product
+        PEM_TRY(pem_tiled_build_views(ctx, A, true, false));
+        PEM_TRY(pem_tiled_build_views(ctx, B, true, false));
+    }
     KT_BEGIN(KT_NUMERIC);
-    if (C->nnz > 0 && C->s3_tiles) {
+    if (C->nnz > 0 && C->s3_rows) {
+        const int64_t nblk = (C->tiles * 16 + S3R_THREADS - 1) / S3R_THREADS;
+        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^35 tiles");
+        k_step3_rows<<<(unsigned)nblk, S3R_THREADS, 0, ctx->stream>>>(
+            C->tiles, C->pair_ptr, C->pair_list, C->masks, C->tile_nnz_ptr,
+            A->tile_nnz_ptr, A->vals, A->row_rec, B->tile_nnz_ptr, B->vals, B->row_rec, C->vals);
+        PEM_LAUNCHED();
+    } else if (C->nnz > 0 && C->s3_tiles) {
         const int64_t nblk = (C->tiles * 32 + S3W_THREADS - 1) / S3W_THREADS;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^34 tiles");
         k_step3_tiles<<<(unsigned)nblk, S3W_THREADS, 0, ctx->stream>>>(

@@ -473,10 +473,11 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
             // one record per A tile row / B tile column: mask | offset of its first value << 16
             const unsigned ar = A_row_rec[(unsigned)ab.x * 16u + r];
             const unsigned bc = B_col_rec[(unsigned)ab.y * 16u + c];
+            const unsigned ao = A_off[ab.x], bo = B_off[ab.y];      // issued with the records, not after the mask test
             unsigned m = ar & bc & 0xFFFFu;
             if (m) {
-                const double* __restrict__ av = A_vals + (A_off[ab.x] + (ar >> 16));        // row r of the A tile
-                const double* __restrict__ bv = B_vals_t + (B_off[ab.y] + (bc >> 16));      // column c of the B tile
+                const double* __restrict__ av = A_vals + (ao + (ar >> 16));        // row r of the A tile
+                const double* __restrict__ bv = B_vals_t + (bo + (bc >> 16));      // column c of the B tile
                 do {
                     const unsigned low = m & (0u - m);
                     m ^= low;

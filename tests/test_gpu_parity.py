@@ -369,3 +369,52 @@ def test_config4_full_size_known_answers_and_checksum(engine):
     want = float(np.dot(colsum, rowsum))
     assert abs(s - want) <= 1e-9 * abs(want) and abs(a - want) <= 1e-9 * abs(want)   # all values positive
     C.free(); A.free()
+
+
+def test_fuzz_all_variants_against_oracle(engine):
+    """Seeded sweep over shapes, densities, products and every algorithm variant: step-1 path
+    (bitmap, tile-level / row-sliced expand-sort-compress), step-3 mapping (four kernels), reference-
+    faithful empty tiles on/off, tile-row panels.  Structure and value bits against the host oracle."""
+    rng = np.random.default_rng(2026)
+    for case in range(36):
+        m = int(rng.choice([1, 7, 16, 33, 100, 257, 900]))
+        aat = bool(rng.integers(0, 2))
+        n = int(rng.choice([1, 5, 16, 48, 130, 700, 3000])) if aat else m
+        nnz = int(min(m * n, rng.choice([1, 3, 40, 400, 3000, 12000])))
+        rows, cols, I, J, V = synth.random_sparse(m, n, nnz, seed=1000 + case, integer_values=bool(case % 3 == 0))
+        if case % 5 == 0 and I.size:                      # a dense block somewhere: full tiles, long pair lists
+            k = min(m, n, 20)
+            bi, bj = np.divmod(np.arange(k * k, dtype=np.int32), k)
+            key = np.unique(np.concatenate([I.astype(np.int64) * n + J, bi.astype(np.int64) * n + bj]))
+            I = (key // n).astype(np.int32); J = (key % n).astype(np.int32)
+            V = rng.uniform(-1, 1, I.size)
+        _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, aat)
+        ro, co, vo = oC.to_coo()
+        A = engine.convert_coo(rows, cols, I, J, V)
+        B = engine.transpose(A) if aat else A
+        path = (1, 3, 4)[case % 3]
+        owner = (2, 4, 1, 3)[case % 4]
+        keep = case % 2
+        engine.set_option(pem.OPT_STEP1_PATH, path)
+        engine.set_option(pem.OPT_OWNER, owner)
+        engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep)
+        try:
+            nparts = 1 + case % 3
+            bounds = engine.partition_panels(A, B, nparts)
+            parts = []
+            for p in range(nparts):
+                C = engine.spgemm(A, B, panel=(bounds[p], bounds[p + 1]))
+                parts.append(C.to_coo())
+                C.free()
+        finally:
+            engine.set_option(pem.OPT_STEP1_PATH, 0)
+            engine.set_option(pem.OPT_OWNER, 0)
+            engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+        r = np.concatenate([x[0] for x in parts]); c = np.concatenate([x[1] for x in parts])
+        v = np.concatenate([x[2] for x in parts])
+        tag = f"case {case}: {m}x{n} nnz {I.size} aat {aat} path {path} owner {owner} keep {keep} parts {nparts}"
+        assert np.array_equal(r, ro) and np.array_equal(c, co), tag
+        assert np.array_equal(v, vo), tag
+        if B is not A:
+            B.free()
+        A.free()

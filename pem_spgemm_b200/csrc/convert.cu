@@ -518,6 +518,8 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         ++ctx->launches;
         CV_CK(cudaGetLastError());
         CV_CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        T->h_tile_row_ptr.resize((size_t)T->tile_rows + 1);
+        CV_CK(cudaMemcpyAsync(T->h_tile_row_ptr.data(), T->tile_row_ptr, ((size_t)T->tile_rows + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CV_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CV_CK(cudaStreamSynchronize(ctx->stream));
         pem_free(ctx, keys_sorted);
@@ -530,6 +532,7 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         CV_TRY(pem_alloc(ctx, &T->row_ptr, 0)); CV_TRY(pem_alloc(ctx, &T->tile_col_idx, 0));
         CV_TRY(pem_alloc(ctx, &T->tile_row_idx, 0)); CV_TRY(pem_alloc(ctx, &T->col_occ, 0)); CV_TRY(pem_alloc(ctx, &T->row_occ, 0));
         CV_TRY(pem_alloc(ctx, &T->rc_idx, 0));
+        T->h_tile_row_ptr.assign((size_t)T->tile_rows + 1, 0);
         CV_CK(cudaStreamSynchronize(ctx->stream));
     }
 #undef CV_TRY
@@ -638,6 +641,7 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
     TR_TRY(pem_alloc(ctx, &T->col_occ, n)); TR_TRY(pem_alloc(ctx, &T->row_occ, n));
     if (n == 0) {
         TR_CK(cudaMemsetAsync(T->tile_nnz_ptr, 0, 4, ctx->stream));
+        T->h_tile_row_ptr.assign((size_t)T->tile_rows + 1, 0);
         *out = T;
         return PEM_OK;
     }
@@ -663,6 +667,9 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
         T->tile_row_ptr, T->col_occ, T->row_occ, T->rc_idx, T->vals);
     ++ctx->launches;
     TR_CK(cudaGetLastError());
+    T->h_tile_row_ptr.resize((size_t)T->tile_rows + 1);
+    TR_CK(cudaMemcpyAsync(T->h_tile_row_ptr.data(), T->tile_row_ptr, ((size_t)T->tile_rows + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TR_CK(cudaStreamSynchronize(ctx->stream));
 #undef TR_TRY
 #undef TR_CK
     pem_free(ctx, keys); pem_free(ctx, keys2); pem_free(ctx, ids); pem_free(ctx, perm); pem_free(ctx, nptr); pem_free(ctx, tmp);

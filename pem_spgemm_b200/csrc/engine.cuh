@@ -7,6 +7,7 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "pemspgemm.h"
 
@@ -113,6 +114,7 @@ struct pem_tiled {
     uint16_t* col_occ = nullptr;      // [tiles]
     uint16_t* row_occ = nullptr;      // [tiles]
     uint8_t* rc_idx = nullptr;        // [nnz] (r<<4)|c of every value, tile-major (the reference's *tiles_rowColIdx)
+    std::vector<int32_t> h_tile_row_ptr;  // host copy of tile_row_ptr: panel calls find their tile range without a device read
     // row slices, built on first use as a B operand of step 1 (pem_tiled_build_srow): for every
     // matrix row s the ids of the tiles that hold a nonzero of row s, in tile-column order
     int64_t* srow_ptr = nullptr;      // [rows16+1], rows16 = 16*tile_rows

@@ -516,7 +516,10 @@ int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_resu
     if (nrows == 0 || A->tiles == 0 || B->tiles == 0) return PEM_OK;
     // A tiles of the panel
     int p0 = 0, p1 = A->tiles;
-    if (rb != 0 || re != A->tile_rows) {
+    if ((rb != 0 || re != A->tile_rows) && A->h_tile_row_ptr.size() == (size_t)A->tile_rows + 1) {
+        p0 = A->h_tile_row_ptr[(size_t)rb];      // host copy kept by the conversion: no device read, no sync
+        p1 = A->h_tile_row_ptr[(size_t)re];
+    } else if (rb != 0 || re != A->tile_rows) {
         int32_t h[2];
         PEM_CK(cudaMemcpyAsync(&h[0], A->tile_row_ptr + rb, 4, cudaMemcpyDeviceToHost, ctx->stream));
         PEM_CK(cudaMemcpyAsync(&h[1], A->tile_row_ptr + re, 4, cudaMemcpyDeviceToHost, ctx->stream));

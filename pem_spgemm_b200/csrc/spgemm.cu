@@ -231,7 +231,7 @@ k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t
 // The products of a tile's pairs are OR-reduced by a segmented warp scan (pairs of a tile are
 // consecutive lanes); a run that lies inside one warp is stored, a run cut by a warp boundary is
 // merged with atomicOr into the zero-initialised mask array.
-__global__ void __launch_bounds__(S2P_THREADS)
+__global__ void __launch_bounds__(S2P_THREADS, 8)
 k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
               const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
               const uint32_t* __restrict__ A_off, const uint8_t* __restrict__ A_rc,

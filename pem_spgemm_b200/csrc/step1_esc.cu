@@ -188,7 +188,7 @@ k_merge_split(int nchunks, int np, int64_t P, const int64_t* __restrict__ pptr, 
 // SLICED: the work items are (A tile, column) pairs over B's row slices (k_items) instead of A tiles
 // over B' rows; item_p / srow_tile translate item -> A tile and slice position -> B tile.
 template <class KeyT, int MODE, bool SLICED>
-__global__ void __launch_bounds__(EX_THREADS)
+__global__ void __launch_bounds__(EX_THREADS, 6)
 k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, const int32_t* __restrict__ split,
          const int32_t* __restrict__ bfirst, const uint16_t* __restrict__ item_mask,
          const int32_t* __restrict__ item_p, const int32_t* __restrict__ srow_tile,

@@ -208,29 +208,21 @@ k_srow_count(const uint16_t* __restrict__ row_occ, const int32_t* __restrict__ t
     }
 }
 
-// fill: warp per tile row; the row's tiles are visited 32 at a time in tile-column order and every
-// occupied (tile, row) places the tile id at ballot rank, so each slice keeps tile-column order
+// fill: thread per tile; every occupied row of the tile claims the next slot of its slice.  The order
+// of the tiles inside a slice is irrelevant: step 1 sorts the expanded pairs by (C' row, tile column)
+// and two tiles of one slice never share a tile column, so the result does not depend on it.
 __global__ void __launch_bounds__(256)
-k_srow_fill(int tile_rows, const int32_t* __restrict__ tile_row_ptr, const uint16_t* __restrict__ row_occ,
-            const int64_t* __restrict__ srow_ptr, int32_t* __restrict__ srow_tile)
+k_srow_fill(const uint16_t* __restrict__ row_occ, const int32_t* __restrict__ tile_row, int cnt,
+            const int64_t* __restrict__ srow_ptr, unsigned* __restrict__ cursor, int32_t* __restrict__ srow_tile)
 {
-    const int tr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (tr >= tile_rows) return;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int ts = tile_row_ptr[tr], te = tile_row_ptr[tr + 1];
-    int64_t at[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) at[r] = srow_ptr[(size_t)tr * 16 + r];
-    for (int q0 = ts; q0 < te; q0 += 32) {
-        const int q = q0 + lane;
-        const unsigned occ = q < te ? (unsigned)row_occ[q] : 0u;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (occ >> r) & 1u);
-            if ((occ >> r) & 1u) srow_tile[at[r] + __popc(bal & lt)] = q;
-            at[r] += __popc(bal);
-        }
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    unsigned occ = row_occ[t];
+    const size_t base = (size_t)tile_row[t] * 16;
+    while (occ) {
+        const int r = __ffs(occ) - 1;
+        occ &= occ - 1;
+        srow_tile[srow_ptr[base + r] + atomicAdd(&cursor[base + r], 1u)] = t;
     }
 }
 
@@ -570,9 +562,12 @@ int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* Bc)
     int32_t* tl = nullptr;
     PEM_TRY(pem_alloc(ctx, &tl, (size_t)total));
     if (B->tiles) {
-        k_srow_fill<<<pem_div_up((int64_t)B->tile_rows * 32, 256), 256, 0, ctx->stream>>>(
-            B->tile_rows, B->tile_row_ptr, B->row_occ, ptr, tl);
+        unsigned* cursor = nullptr;
+        PEM_TRY(pem_alloc(ctx, &cursor, rows16));
+        PEM_CK(cudaMemsetAsync(cursor, 0, rows16 * 4, ctx->stream));
+        k_srow_fill<<<pem_div_up(B->tiles, 256), 256, 0, ctx->stream>>>(B->row_occ, B->tile_row_idx, B->tiles, ptr, cursor, tl);
         PEM_LAUNCHED();
+        pem_free(ctx, cursor);
     }
     B->srow_ptr = ptr;
     B->srow_total = total;

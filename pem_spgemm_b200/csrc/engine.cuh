@@ -116,7 +116,7 @@ struct pem_tiled {
     uint8_t* rc_idx = nullptr;        // [nnz] (r<<4)|c of every value, tile-major (the reference's *tiles_rowColIdx)
     std::vector<int32_t> h_tile_row_ptr;  // host copy of tile_row_ptr: panel calls find their tile range without a device read
     // row slices, built on first use as a B operand of step 1 (pem_tiled_build_srow): for every
-    // matrix row s the ids of the tiles that hold a nonzero of row s, in tile-column order
+    // matrix row s the ids of the tiles that hold a nonzero of row s (in no particular order)
     int64_t* srow_ptr = nullptr;      // [rows16+1], rows16 = 16*tile_rows
     int32_t* srow_tile = nullptr;     // [srow_ptr[rows16]]
     int64_t srow_total = 0;

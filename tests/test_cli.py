@@ -78,3 +78,15 @@ def test_cli_report_csv_and_dump(tmp_path, aat):
     out = _run([mtx, "0"] + (["1"] if aat else []), tmp_path, env)      # second run appends
     assert out.returncode == 0 and "Not saving results. Exiting." in out.stdout
     assert open(tmp_path / "pemspgemm_benchmark_result.csv").read().count("\n") == 2
+
+
+@pytest.mark.gpu
+def test_cpp_abi_client(tmp_path):
+    """examples/abi_demo.cpp: a C++ program that uses only include/pemspgemm.h (the Laplacian is
+    symmetric, so A*A^T through pem_tiled_transpose must equal A^2; figures for the 256 grid are the
+    pinned config-1 answers of SURVEY.md section 8c)."""
+    demo = os.path.join(os.path.dirname(pem.CLI_PATH), "abi_demo")
+    out = subprocess.run([demo, "256"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "nnzA=326656 flop=1629192 C_tiles=43364 C_nnz=846852 sum=1032.0 abs_sum=4178952.0 C[0,0]=18.0" in out.stdout
+    assert "A*A^T: C_nnz=846852 sum=1032.0 abs_sum=4178952.0" in out.stdout

@@ -111,6 +111,9 @@ int64_t pem_ctx_launch_count(const pem_ctx* ctx);
  * the last pem_spgemm / pem_spgemm_panel call: [0] k_expand (step 1 product expansion), [1] the
  * step-1 radix sort, [2] k_step2_pairs, [3] the step-3 numeric kernel.  Returns the count (4). */
 int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n);
+/* Allocations that missed the context's block cache and went to the CUDA pool since creation
+ * (diagnostic: a steady-state loop should not add any). */
+int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx);
 /* Bytes currently reserved by the context's pool (diagnostic). */
 int64_t pem_ctx_pool_bytes(const pem_ctx* ctx);
 

@@ -69,7 +69,7 @@ class ResultInfo(C.Structure):
 
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
-    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_kernel_ms", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
+    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
     "pem_tiled_info_get",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
@@ -106,6 +106,7 @@ def load():
         "pem_ctx_sync": (C.c_int, [vp]),
         "pem_ctx_launch_count": (i64, [vp]),
         "pem_ctx_pool_bytes": (i64, [vp]),
+        "pem_ctx_pool_mallocs": (i64, [vp]),
         "pem_ctx_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
         "pem_convert_coo": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
         "pem_tiled_transpose": (C.c_int, [vp, vp, C.POINTER(vp)]),
@@ -195,6 +196,10 @@ class Context:
         a = (C.c_double * 4)()
         load().pem_ctx_kernel_ms(self._h, a, 4)
         return {"k_expand": a[0], "radix_sort": a[1], "k_step2_pairs": a[2], "step3_numeric": a[3]}
+
+    @property
+    def pool_mallocs(self) -> int:
+        return int(load().pem_ctx_pool_mallocs(self._h))
 
     @property
     def pool_bytes(self) -> int:

@@ -34,7 +34,7 @@ inline int h_bits_for(int64_t n)
 __global__ void __launch_bounds__(256)
 k_make_keys(const int32_t* __restrict__ I, const int32_t* __restrict__ J, int64_t nnz,
             int rows, int cols, int transpose, int cb, uint64_t* __restrict__ keys,
-            int64_t* __restrict__ scalars)
+            uint32_t* __restrict__ pos, int64_t* __restrict__ scalars)
 {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -49,15 +49,22 @@ k_make_keys(const int32_t* __restrict__ I, const int32_t* __restrict__ J, int64_
             key = ((uint64_t)(i >> 4) << (cb + 8)) | ((uint64_t)(j >> 4) << 8) | (uint64_t)(((i & 15) << 4) | (j & 15));
         }
         keys[e] = key;
+        pos[e] = (uint32_t)e;
     }
 }
 
-// (r<<4)|c of every value = low byte of its sorted key
+// (r<<4)|c of every value = low byte of its sorted key; the value itself is fetched through the
+// sorted original position (the sort carries 4-byte positions, not 8-byte values, and the values'
+// host->device copy overlaps it)
 __global__ void __launch_bounds__(256)
-k_rc_idx(const uint64_t* __restrict__ keys, int64_t nnz, uint8_t* __restrict__ rc)
+k_rc_idx_vals(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, const double* __restrict__ V,
+              int64_t nnz, uint8_t* __restrict__ rc, double* __restrict__ vals)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < nnz) rc[e] = (uint8_t)(keys[e] & 255u);
+    if (e < nnz) {
+        rc[e] = (uint8_t)(keys[e] & 255u);
+        vals[e] = V[pos[e]];
+    }
 }
 
 // predicate for the tile census: position e starts a new tile
@@ -445,24 +452,31 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
             CV_TRY(pem_alloc(ctx, &dV, (size_t)nnz));
             CV_CK(cudaMemcpyAsync(dI, I, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
             CV_CK(cudaMemcpyAsync(dJ, J, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-            CV_CK(cudaMemcpyAsync(dV, V, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+            // the values travel on a second stream, behind the coordinates and under key generation + sort
+            CV_CK(cudaEventRecord(ctx->ev_copy[0], ctx->stream));
+            CV_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
+            CV_CK(cudaMemcpyAsync(dV, V, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CV_CK(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
         } else {
             dI = const_cast<int32_t*>(I); dJ = const_cast<int32_t*>(J); dV = const_cast<double*>(V);
         }
         uint64_t *keys = nullptr, *keys_sorted = nullptr;
+        uint32_t *pos = nullptr, *pos_sorted = nullptr;
         CV_TRY(pem_alloc(ctx, &keys, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &keys_sorted, (size_t)nnz));
+        CV_TRY(pem_alloc(ctx, &pos, (size_t)nnz));
+        CV_TRY(pem_alloc(ctx, &pos_sorted, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &T->vals, (size_t)nnz));
         CV_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
 
         int grid = (int)std::min<int64_t>(pem_div_up(nnz, 256), (int64_t)ctx->sm_count * 32);
-        k_make_keys<<<grid, 256, 0, ctx->stream>>>(dI, dJ, nnz, rows, cols, transpose, cb, keys, ctx->d_scalars);
+        k_make_keys<<<grid, 256, 0, ctx->stream>>>(dI, dJ, nnz, rows, cols, transpose, cb, keys, pos, ctx->d_scalars);
         ++ctx->launches;
         CV_CK(cudaGetLastError());
 
-        // one radix sort of (key, value) over the bits in use
+        // one radix sort of (key, original position) over the bits in use
         size_t tmp_bytes = 0, tmp2 = 0;
-        CV_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, dV, T->vals, nnz, 0, 8 + cb + rb, ctx->stream));
+        CV_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, pos, pos_sorted, nnz, 0, 8 + cb + rb, ctx->stream));
         uint32_t* start_tmp = nullptr;
         CV_TRY(pem_alloc(ctx, &start_tmp, (size_t)nnz + 1));
         cub::CountingInputIterator<uint32_t> iota(0);
@@ -471,8 +485,15 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         CV_CK(cub::DeviceSelect::If(nullptr, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
         char* tmp = nullptr;
         CV_TRY(pem_alloc(ctx, &tmp, std::max(tmp_bytes, tmp2)));
-        CV_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, dV, T->vals, nnz, 0, 8 + cb + rb, ctx->stream));
+        CV_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, pos, pos_sorted, nnz, 0, 8 + cb + rb, ctx->stream));
         CV_CK(cub::DeviceSelect::If(tmp, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
+        if (own) CV_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));     // the values have arrived
+        CV_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)nnz));
+        k_rc_idx_vals<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(keys_sorted, pos_sorted, dV, nnz, T->rc_idx, T->vals);
+        ++ctx->launches;
+        CV_CK(cudaGetLastError());
+        pem_free(ctx, pos);
+        pem_free(ctx, pos_sorted);
         CV_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CV_CK(cudaStreamSynchronize(ctx->stream));
         pem_free(ctx, tmp);
@@ -499,10 +520,6 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         CV_TRY(pem_alloc(ctx, &T->tile_row_idx, n));
         CV_TRY(pem_alloc(ctx, &T->col_occ, n));
         CV_TRY(pem_alloc(ctx, &T->row_occ, n));
-        CV_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)nnz));
-        k_rc_idx<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(keys_sorted, nnz, T->rc_idx);
-        ++ctx->launches;
-        CV_CK(cudaGetLastError());
         CV_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         k_build_tiles<<<pem_div_up(cnt, 128), 128, 0, ctx->stream>>>(
             keys_sorted, T->tile_nnz_ptr, (int)cnt, (uint32_t)nnz, cb, T->tile_rows, T->masks, T->masks_t,

@@ -39,6 +39,7 @@ int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
     if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
     ctx->live_blocks[*p] = bytes;
     ctx->pool_taken += bytes;
+    ++ctx->pool_mallocs;
     return PEM_OK;
 }
 
@@ -88,6 +89,9 @@ int pem_ctx_create(pem_ctx** out, int device)
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    for (auto& ev : ctx->ev_copy)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     cudaMemPoolProps props = {};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
@@ -128,6 +132,9 @@ void pem_ctx_destroy(pem_ctx* ctx)
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    for (auto& ev : ctx->ev_copy)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -168,6 +175,8 @@ int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n)
     for (int i = 0; i < KT_N; ++i) ms[i] = ctx->kt_ms[i];
     return KT_N;
 }
+
+int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx) { return ctx ? ctx->pool_mallocs : 0; }
 
 int64_t pem_ctx_pool_bytes(const pem_ctx* ctx)
 {

@@ -21,6 +21,8 @@ enum { KT_EXPAND = 0, KT_SORT = 1, KT_PAIRS = 2, KT_NUMERIC = 3, KT_N = 4 };
 struct pem_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host->device copy of the values, overlapped with key generation and the sort
+    cudaEvent_t ev_copy[2] = {};
     cudaMemPool_t pool = nullptr;
     std::string err;
     int64_t launches = 0;        // kernels of this library launched on the stream
@@ -40,6 +42,7 @@ struct pem_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live_blocks;
     size_t cached_bytes = 0, cache_limit = (size_t)32 << 30;
+    int64_t pool_mallocs = 0;    // cudaMallocFromPoolAsync calls (cache misses) since creation
     size_t pool_taken = 0;       // bytes this context holds from its pool (live + cached)
     size_t free_at_create = 0;   // device memory free when the context was created (cudaMemGetInfo costs ~1 ms: never on the hot path)
 

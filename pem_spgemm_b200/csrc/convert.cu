@@ -432,7 +432,11 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     T->rows = rows; T->cols = cols; T->nnz = nnz;
     T->tile_rows = (int32_t)(((int64_t)rows + PEM_TILE - 1) / PEM_TILE);
     T->tile_cols = (int32_t)(((int64_t)cols + PEM_TILE - 1) / PEM_TILE);
-    auto fail = [&](int rc) { pem_tiled_free(ctx, T); return rc; };
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(ctx->copy_stream);    // nothing may still be writing a buffer that goes back to the cache
+        pem_tiled_free(ctx, T);
+        return rc;
+    };
 #define CV_TRY(expr) do { int rc_ = (expr); if (rc_ != PEM_OK) return fail(rc_); } while (0)
 #define CV_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx->fail_cuda(e_, #call, __FILE__, __LINE__)); } while (0)
 

@@ -15,6 +15,9 @@
 // context
 // ---------------------------------------------------------------------------------------
 enum { PEM_NSCALARS = 24, PEM_NEVENTS = 8 };
+// pairs per block of step 2's pair kernel; step 1 (k_ctiles) emits the first tile of every such block
+constexpr int PEM_PAIR_BLOCK = 128;
+
 // kernels timed individually (CUDA events on the context's stream) for the roofline report
 enum { KT_EXPAND = 0, KT_SORT = 1, KT_PAIRS = 2, KT_NUMERIC = 3, KT_N = 4 };
 

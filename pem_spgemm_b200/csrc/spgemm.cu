@@ -206,9 +206,9 @@ k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int
 //           one warp per C' tile (k_step3_tiles) when they are dense.
 // =========================================================================================
 
-// first tile of every 256-pair step-2 block (every C' tile owns >= 1 pair, so a block overlaps
-// at most 257 tiles)
-constexpr int S2P_THREADS = 256;
+// first tile of every PEM_PAIR_BLOCK-pair step-2 block (every C' tile owns >= 1 pair, so a block overlaps
+// at most PEM_PAIR_BLOCK + 1 tiles)
+constexpr int S2P_THREADS = PEM_PAIR_BLOCK;
 __global__ void __launch_bounds__(256)
 k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t* __restrict__ blk_tile)
 {
@@ -231,7 +231,7 @@ k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t
 // The products of a tile's pairs are OR-reduced by a segmented warp scan (pairs of a tile are
 // consecutive lanes); a run that lies inside one warp is stored, a run cut by a warp boundary is
 // merged with atomicOr into the zero-initialised mask array.
-__global__ void __launch_bounds__(S2P_THREADS, 8)
+__global__ void __launch_bounds__(S2P_THREADS, 2048 / S2P_THREADS)
 k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
               const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
               const uint32_t* __restrict__ A_off, const uint8_t* __restrict__ A_rc,

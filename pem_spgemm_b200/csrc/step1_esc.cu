@@ -328,9 +328,9 @@ k_ctiles(int64_t ntiles, int64_t npairs, int nrows, int rb, int wbits, const Key
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     const int64_t h = heads[t];
-    {   // first tile of every 256-pair block of step 2 (a tile owning pairs [h, hn) opens the blocks that start inside)
+    {   // first tile of every PEM_PAIR_BLOCK-pair block of step 2 (a tile owning pairs [h, hn) opens the blocks that start inside)
         const int64_t hn = t + 1 < ntiles ? heads[t + 1] : npairs;
-        for (int64_t b = (h + 255) / 256; b * 256 < hn; ++b) pair_blk[b] = (int32_t)t;
+        for (int64_t b = (h + PEM_PAIR_BLOCK - 1) / PEM_PAIR_BLOCK; b * PEM_PAIR_BLOCK < hn; ++b) pair_blk[b] = (int32_t)t;
     }
     const KeyT key = keys[h];
     const int row = (int)(key >> wbits);
@@ -488,7 +488,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     E_TRY(pem_alloc(ctx, &C->tile_col, (size_t)T));
     E_TRY(pem_alloc(ctx, &C->pair_ptr, (size_t)T + 1));
     pem_free(ctx, C->pair_blk);
-    E_TRY(pem_alloc(ctx, &C->pair_blk, (size_t)((F + 255) / 256) + 1));
+    E_TRY(pem_alloc(ctx, &C->pair_blk, (size_t)((F + PEM_PAIR_BLOCK - 1) / PEM_PAIR_BLOCK) + 1));
     k_ctiles<KeyT><<<pem_div_up(T, 256), 256, 0, ctx->stream>>>(T, F, nrows, rb, wbits, key_a, heads, jmin, C->pair_ptr,
                                                                 C->tile_row, C->tile_col, C->row_ptr, C->pair_blk);
     E_LAUNCHED();

@@ -311,6 +311,75 @@ k_compact(const int32_t* __restrict__ split, const int64_t* __restrict__ chunk_o
     }
 }
 
+// ---- block-local sort of short rows --------------------------------------------------------------------
+// The compacted pairs are grouped by C' row in row order (products are expanded in A-tile order):
+// off[r] = first pair of row r (lower bound of r among the keys' row fields), off[nrows] = F.
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+k_row_offsets(int nrows, int npairs, int wbits, const KeyT* __restrict__ keys, int* __restrict__ off)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nrows) return;
+    int lo = 0, hi = npairs;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)(keys[mid] >> wbits) < (int64_t)r) lo = mid + 1; else hi = mid;
+    }
+    off[r] = lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_max_segment(int nrows, const int* __restrict__ off, int64_t* __restrict__ scalars)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = r < nrows ? off[r + 1] - off[r] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax((long long*)&scalars[SC_MAXD], (long long)len);
+}
+
+// One block per C' row of at most RS_MAX pairs: the row's (tile column, position) words are sorted by a
+// bitonic network in shared memory - position in the low bits makes the words distinct, so the order of
+// equal tile columns is the expansion order (ascending A tile), as a stable sort would give - and the
+// pairs are written out through the sorted positions.  One pass over the data where the radix sort
+// needs one per digit; for banded / stencil matrices (a few hundred pairs per row).
+constexpr int RS_THREADS = 128;
+constexpr int RS_MAX = 1024;          // pairs per row the block sort takes
+constexpr int RS_POS_BITS = 10;
+template <class KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+k_row_sort(int wbits, const int* __restrict__ off, const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
+           KeyT* __restrict__ out_key, int2* __restrict__ out_val)
+{
+    __shared__ unsigned sk[RS_MAX];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int s = off[r], n = off[r + 1] - s;
+    if (n == 0) return;                                  // uniform over the block
+    int N = 2;
+    while (N < n) N <<= 1;
+    const KeyT jmask = ((KeyT)1 << wbits) - 1;
+    for (int i = tid; i < N; i += RS_THREADS)
+        sk[i] = i < n ? ((unsigned)(in_key[s + i] & jmask) << RS_POS_BITS) | (unsigned)i : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (N >> 1); t += RS_THREADS) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // element with bit j clear
+                const int hi = lo | j;
+                const unsigned a = sk[lo], b = sk[hi];
+                const bool up = (lo & k) == 0;
+                if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    const KeyT rowbits = (KeyT)(unsigned)r << wbits;
+    for (int i = tid; i < n; i += RS_THREADS) {
+        const unsigned e = sk[i];
+        out_key[s + i] = rowbits | (KeyT)(e >> RS_POS_BITS);
+        out_val[s + i] = in_val[s + (int)(e & ((1u << RS_POS_BITS) - 1u))];
+    }
+}
+
 template <class KeyT>
 struct RunHead {
     const KeyT* keys;
@@ -379,7 +448,9 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     int2 *val_a = nullptr, *val_b = nullptr;
     char* tmp = nullptr;
     int64_t* heads = nullptr;
+    int* seg_off = nullptr;
     auto cleanup = [&]() {
+        pem_free(ctx, seg_off);
         pem_free(ctx, split); pem_free(ctx, chunk_off); pem_free(ctx, key_a); pem_free(ctx, key_b);
         pem_free(ctx, val_a); pem_free(ctx, val_b); pem_free(ctx, tmp); pem_free(ctx, heads);
     };
@@ -443,10 +514,30 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
             B->row_occ, jmin, wbits, ctx->opt_keep_empty, chunk_off, nullptr, key_a, val_a);
         E_LAUNCHED();
     }
-    // stable radix sort by (row, column) over the bits in use
     E_TRY(pem_alloc(ctx, &key_b, (size_t)F));
     E_TRY(pem_alloc(ctx, &val_b, (size_t)F));
-    {
+    // Short rows (banded / stencil matrices) are sorted row by row in shared memory: one pass over the
+    // pairs.  Power-law inputs have rows of millions of pairs and keep the global radix sort.
+    bool by_rows = false;
+    if (F < 0x7fffffffLL && wbits + RS_POS_BITS <= 32 && !getenv("PEM_ESC_NO_ROWSORT")) {
+        E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
+        E_CK(cudaMemsetAsync(ctx->d_scalars + SC_MAXD, 0, 8, ctx->stream));
+        k_row_offsets<KeyT><<<pem_div_up((int64_t)nrows + 1, 256), 256, 0, ctx->stream>>>(nrows, (int)F, wbits, key_a, seg_off);
+        E_LAUNCHED();
+        k_max_segment<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, seg_off, ctx->d_scalars);
+        E_LAUNCHED();
+        E_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        E_CK(cudaStreamSynchronize(ctx->stream));
+        by_rows = ctx->h_scalars[0] <= RS_MAX;
+    }
+    if (by_rows) {
+        KT_BEGIN(KT_SORT);
+        k_row_sort<KeyT><<<nrows, RS_THREADS, 0, ctx->stream>>>(wbits, seg_off, key_a, val_a, key_b, val_b);
+        KT_END(KT_SORT);
+        E_LAUNCHED();
+        std::swap(key_a, key_b);
+        std::swap(val_a, val_b);
+    } else {   // stable radix sort by (row, column) over the bits in use
         cub::DoubleBuffer<KeyT> dk(key_a, key_b);
         cub::DoubleBuffer<unsigned long long> dv((unsigned long long*)val_a, (unsigned long long*)val_b);
         size_t tb = 0;

@@ -316,16 +316,20 @@ def test_esc_count_then_write_variant(engine, k):
     A = engine.convert_coo(rows, cols, I, J, V)
     got = {}
     for two_pass in ("0", "1"):
-        os.environ["PEM_ESC_TWO_PASS"] = two_pass
-        try:
-            for path in (3, 4):
-                engine.set_option(pem.OPT_STEP1_PATH, path)
-                C = engine.spgemm(A, A)
-                got[(two_pass, path)] = [C.array(x) for x in ("row_ptr", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "vals")]
-                C.free()
-        finally:
-            os.environ.pop("PEM_ESC_TWO_PASS", None)
-            engine.set_option(pem.OPT_STEP1_PATH, 0)
+        for no_rowsort in ("", "1"):            # block-local row sort (short rows) vs. global radix sort
+            os.environ["PEM_ESC_TWO_PASS"] = two_pass
+            if no_rowsort:
+                os.environ["PEM_ESC_NO_ROWSORT"] = "1"
+            try:
+                for path in (3, 4):
+                    engine.set_option(pem.OPT_STEP1_PATH, path)
+                    C = engine.spgemm(A, A)
+                    got[(two_pass + no_rowsort, path)] = [C.array(x) for x in ("row_ptr", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "vals")]
+                    C.free()
+            finally:
+                os.environ.pop("PEM_ESC_TWO_PASS", None)
+                os.environ.pop("PEM_ESC_NO_ROWSORT", None)
+                engine.set_option(pem.OPT_STEP1_PATH, 0)
     ref = got[("0", 3)]
     for key, arrs in got.items():
         for a, b in zip(ref, arrs):

@@ -338,32 +338,29 @@ k_max_segment(int nrows, const int* __restrict__ off, int64_t* __restrict__ scal
     if ((threadIdx.x & 31) == 0 && len > 0) atomicMax((long long*)&scalars[SC_MAXD], (long long)len);
 }
 
-// One block per C' row of at most RS_MAX pairs: the row's (tile column, position) words are sorted by a
+// One block per C' row: the row's (tile column, position) words are sorted by a
 // bitonic network in shared memory - position in the low bits makes the words distinct, so the order of
 // equal tile columns is the expansion order (ascending A tile), as a stable sort would give - and the
 // pairs are written out through the sorted positions.  One pass over the data where the radix sort
 // needs one per digit; for banded / stencil matrices (a few hundred pairs per row).
-constexpr int RS_THREADS = 128;
-constexpr int RS_MAX = 1024;          // pairs per row the block sort takes
-constexpr int RS_POS_BITS = 10;
-template <class KeyT>
-__global__ void __launch_bounds__(RS_THREADS)
+template <class KeyT, int THREADS, int POS_BITS>
+__global__ void __launch_bounds__(THREADS)
 k_row_sort(int wbits, const int* __restrict__ off, const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
            KeyT* __restrict__ out_key, int2* __restrict__ out_val)
 {
-    __shared__ unsigned sk[RS_MAX];
+    extern __shared__ unsigned sk[];
     const int r = blockIdx.x, tid = threadIdx.x;
     const int s = off[r], n = off[r + 1] - s;
     if (n == 0) return;                                  // uniform over the block
     int N = 2;
     while (N < n) N <<= 1;
     const KeyT jmask = ((KeyT)1 << wbits) - 1;
-    for (int i = tid; i < N; i += RS_THREADS)
-        sk[i] = i < n ? ((unsigned)(in_key[s + i] & jmask) << RS_POS_BITS) | (unsigned)i : 0xFFFFFFFFu;
+    for (int i = tid; i < N; i += THREADS)
+        sk[i] = i < n ? ((unsigned)(in_key[s + i] & jmask) << POS_BITS) | (unsigned)i : 0xFFFFFFFFu;
     __syncthreads();
     for (int k = 2; k <= N; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (N >> 1); t += RS_THREADS) {
+            for (int t = tid; t < (N >> 1); t += THREADS) {
                 const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // element with bit j clear
                 const int hi = lo | j;
                 const unsigned a = sk[lo], b = sk[hi];
@@ -373,12 +370,13 @@ k_row_sort(int wbits, const int* __restrict__ off, const KeyT* __restrict__ in_k
             __syncthreads();
         }
     const KeyT rowbits = (KeyT)(unsigned)r << wbits;
-    for (int i = tid; i < n; i += RS_THREADS) {
+    for (int i = tid; i < n; i += THREADS) {
         const unsigned e = sk[i];
-        out_key[s + i] = rowbits | (KeyT)(e >> RS_POS_BITS);
-        out_val[s + i] = in_val[s + (int)(e & ((1u << RS_POS_BITS) - 1u))];
+        out_key[s + i] = rowbits | (KeyT)(e >> POS_BITS);
+        out_val[s + i] = in_val[s + (int)(e & ((1u << POS_BITS) - 1u))];
     }
 }
+constexpr int RS_SMALL = 1024, RS_SMALL_BITS = 10;
 
 template <class KeyT>
 struct RunHead {
@@ -518,8 +516,8 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     E_TRY(pem_alloc(ctx, &val_b, (size_t)F));
     // Short rows (banded / stencil matrices) are sorted row by row in shared memory: one pass over the
     // pairs.  Power-law inputs have rows of millions of pairs and keep the global radix sort.
-    bool by_rows = false;
-    if (F < 0x7fffffffLL && wbits + RS_POS_BITS <= 32 && !getenv("PEM_ESC_NO_ROWSORT")) {
+    int by_rows = 0;                        // 1: every row holds <= 1024 pairs
+    if (F < 0x7fffffffLL && wbits + RS_SMALL_BITS <= 32 && !getenv("PEM_ESC_NO_ROWSORT")) {
         E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
         E_CK(cudaMemsetAsync(ctx->d_scalars + SC_MAXD, 0, 8, ctx->stream));
         k_row_offsets<KeyT><<<pem_div_up((int64_t)nrows + 1, 256), 256, 0, ctx->stream>>>(nrows, (int)F, wbits, key_a, seg_off);
@@ -528,11 +526,14 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         E_LAUNCHED();
         E_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
         E_CK(cudaStreamSynchronize(ctx->stream));
-        by_rows = ctx->h_scalars[0] <= RS_MAX;
+        const int64_t longest = ctx->h_scalars[0];
+        // (a 1024-thread block sorting up to 32768 pairs of a row was tried for config 3's ~13 K-pair rows:
+        //  4.5 ms against 2.7 ms for the radix sort)
+        if (longest <= RS_SMALL) by_rows = 1;
     }
     if (by_rows) {
         KT_BEGIN(KT_SORT);
-        k_row_sort<KeyT><<<nrows, RS_THREADS, 0, ctx->stream>>>(wbits, seg_off, key_a, val_a, key_b, val_b);
+        k_row_sort<KeyT, 128, RS_SMALL_BITS><<<nrows, 128, RS_SMALL * 4, ctx->stream>>>(wbits, seg_off, key_a, val_a, key_b, val_b);
         KT_END(KT_SORT);
         E_LAUNCHED();
         std::swap(key_a, key_b);

@@ -1,11 +1,14 @@
 // The three SpGEMM steps on tiled operands (one iteration of /root/reference/spgemm.cu:1133-1357).
 //
-//   step 1  tile-level symbolic: lives in step1.cu.
-//   step 2  per-tile bitmask symbolic: C tile masks, per-tile nnz, scan, rowColIdx.  Replaces
-//           pem_spgemm_step2_compute_CMasksAndOffsets (:499-550) and ..._CrowColIdx (:552-591).
-//           Atomic-free.
-//   step 3  numeric: one thread per C nonzero, ascending-k fma chain.  Replaces
-//           pem_spgemm_step3_accumulate (:593-661).  Atomic-free, C written exactly once.
+//   step 1  tile-level symbolic: lives in step1_esc.cu (default) and step1.cu (small operands).
+//   step 2  per-tile bitmask symbolic: C tile masks, per-tile nnz, scan (rowColIdx on request only).
+//           Replaces pem_spgemm_step2_compute_CMasksAndOffsets (:499-550) and ..._CrowColIdx
+//           (:552-591).  Default mapping: one thread per (A tile, B tile) pair (k_step2_pairs).
+//   step 3  numeric: ascending-k fma chain per C nonzero, C written exactly once, no floating-point
+//           atomics.  Replaces pem_spgemm_step3_accumulate (:593-661).  Default mapping: one thread
+//           per C nonzero (k_step3_entries); three more mappings are selectable (PEM_OPT_OWNER) and
+//           bit-identical: row-owner in registers (first block below), tile-owner, row-owner with a
+//           shared-memory accumulator.
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -19,7 +22,7 @@
 namespace {
 
 // =========================================================================================
-// Thread mapping of steps 2 and 3: SIXTEEN LANES PER C' TILE, lane = row r of the tile (two tiles
+// PEM_OPT_OWNER = 1: SIXTEEN LANES PER C' TILE in steps 2 and 3, lane = row r of the tile (two tiles
 // per warp).  The lane owns row r of the C tile, so no two threads ever update the same C entry:
 // atomic-free and, because a lane visits its tile's pairs in list order (ascending k across
 // tiles) and the set bits of Amask[r] in ascending k inside a tile, every C entry is accumulated

@@ -88,6 +88,13 @@ def transpose(A: CSR) -> CSR:
     return CSR(A.cols, A.rows, ptr, idx, val)
 
 
+def row_slice(A: CSR, r0: int, r1: int) -> CSR:
+    """Rows [r0, r1) of A as a CSR of its own (views of idx/val): the oracle side of a tile-row panel."""
+    r0 = max(0, min(r0, A.rows)); r1 = max(r0, min(r1, A.rows))
+    b, e = int(A.ptr[r0]), int(A.ptr[r1])
+    return CSR(r1 - r0, A.cols, np.ascontiguousarray(A.ptr[r0:r1 + 1] - b), A.idx[b:e], A.val[b:e])
+
+
 def flop(A: CSR, B: CSR) -> int:
     return int(lib().oracle_flop(A.rows, A.ptr, A.idx, B.ptr))
 

@@ -17,7 +17,21 @@ CASES = {
     "cage8_a2": (lambda: synth.cage_like(8, 9, 9), False),
     "webbase_small_a2": (lambda: synth.config(2, small=True)[2], False),
     "lap256_a2": (lambda: synth.laplacian2d(256), False),
+    # the reference's NSPARSE hash step 1 (> 16,384 B tile columns, spgemm.cu:1142); produced by the
+    # compute_61-PTX rebuild oracle/_ref/pemspgemm_ref61 (the compute_100 one does not terminate there)
+    "rand300k_a2": (lambda: synth.random_sparse(300_000, 300_000, 60_000, seed=5), False),
+    "lap600_a2": (lambda: synth.laplacian2d(600), False),
+    "webbase270k_a2": (lambda: synth.webbase_like(n=270_007, target_nnz=800_000, max_deg=2000), False),
 }
+
+
+def struct_hash(r, c):
+    """Order-independent 64-bit digest of the (row, col) set (same as tests/golden/make_golden.py)."""
+    x = (r.astype(np.uint64) << np.uint64(32)) | c.astype(np.uint64)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xFF51AFD7ED558CCD)
+    x ^= x >> np.uint64(29)
+    return int(x.sum(dtype=np.uint64))
 
 
 def _load(name):
@@ -44,6 +58,14 @@ def test_oracle_matches_reference_dump(name):
         r, c, v = C.to_coo()
         assert np.array_equal(r, g["rows_c"]) and np.array_equal(c, g["cols_c"])
         np.testing.assert_allclose(v, g["vals_c"], rtol=1e-12, atol=1e-16)
+    elif "struct_hash" in g:
+        r, c, v = C.to_coo()
+        assert struct_hash(r, c) == int(g["struct_hash"])
+
+
+def test_nsparse_path_fixtures_present():
+    """At least one fixture must come from the reference's NSPARSE step-1 path."""
+    assert any(str(_load(n)["step1_path"]) == "NSPARSE" for n in CASES)
 
 
 @pytest.mark.gpu
@@ -69,6 +91,10 @@ def test_engine_matches_reference_dump(engine, name):
         r, c, v = C.to_coo()
         assert np.array_equal(r, g["rows_c"]) and np.array_equal(c, g["cols_c"])
         np.testing.assert_allclose(v, g["vals_c"], rtol=1e-12, atol=1e-16)
+    elif "struct_hash" in g:
+        r, c, v = C.to_coo()
+        assert struct_hash(r, c) == int(g["struct_hash"])
+        np.testing.assert_allclose([v.sum(), np.abs(v).sum()], [float(g["val_sum"]), float(g["val_abs_sum"])], rtol=1e-11)
     C.free()
     if B is not A:
         B.free()

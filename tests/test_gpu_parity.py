@@ -350,6 +350,70 @@ def test_config2_full_size_matches_oracle(engine):
     C.free(); A.free()
 
 
+def _assert_same_C_lowmem(Cres, oC, row0=0):
+    """_assert_same_C for results of hundreds of millions of entries: array by array, without building
+    the oracle's row array (rows are compared through per-row counts)."""
+    r, c, v = Cres.to_coo()
+    assert r.size == oC.nnz
+    assert np.array_equal(c, oC.idx)                                   # structure: bit-exact
+    cnt = np.bincount(r - row0, minlength=oC.rows) if r.size else np.zeros(oC.rows, np.int64)
+    assert cnt.size == oC.rows and np.array_equal(cnt, np.diff(oC.ptr))
+    assert r.size == 0 or bool(np.all(np.diff(r) >= 0))
+    del r, c
+    assert np.array_equal(v, oC.val)                                   # same fma order => same bits (tolerance 1e-12 is implied)
+
+
+def test_config3_full_size_matches_oracle(engine):
+    """BASELINE config 3 at full size (A*A^T, 9.94 M nonzeros, nnz(C) = 81.6 M): structure and values of C
+    against the host oracle, bit for bit."""
+    name, tb, (rows, cols, I, J, V) = synth.config(3)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.transpose(A)
+    C = engine.spgemm(A, B)
+    oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, True)
+    assert engine.count_flop(A, B) == host.flop(oA, oB)
+    assert C.info.nnz == oC.nnz
+    _assert_same_C_lowmem(C, oC)
+    C.free(); B.free(); A.free()
+
+
+def test_config4_full_size_matches_oracle(engine):
+    """BASELINE config 4 at full size (96.9 M nonzeros, nnz(C) = 470 M): every column index and every value
+    bit of C against the host oracle (about 16 GB of host memory for the two COO copies)."""
+    name, tb, (rows, cols, I, J, V) = synth.config(4)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    C = engine.spgemm(A, A)
+    oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, False)
+    del I, J, V
+    assert C.info.nnz == oC.nnz == 470_380_286
+    _assert_same_C_lowmem(C, oC)
+    C.free(); A.free()
+
+
+def test_config5_full_size_matches_oracle_panel_by_panel(engine):
+    """BASELINE config 5 at full size (R-MAT scale 22, 67.1 M nonzeros, nnz(C) = 2.5 G > 2^31): C does not fit
+    one GPU in tiled form, so it is produced in 16 tile-row panels; each panel is compared with the host
+    oracle run on the matching row slice of A (host memory stays bounded by one panel)."""
+    name, tb, (rows, cols, I, J, V) = synth.config(5)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    oA = host.coo_to_csr(rows, cols, I, J, V)
+    del I, J, V
+    assert engine.count_flop(A, A) == host.flop(oA, oA)
+    nparts = 16
+    bounds = engine.partition_panels(A, A, nparts)
+    total = 0
+    for p in range(nparts):
+        rb, re = int(bounds[p]), int(bounds[p + 1])
+        C = engine.spgemm(A, A, panel=(rb, re))
+        oC = host.spgemm(host.row_slice(oA, 16 * rb, 16 * re), oA)
+        _assert_same_C_lowmem(C, oC, row0=16 * rb)
+        total += oC.nnz
+        C.free()
+        del oC
+    assert total > 2**31                    # the reference's int32 C_nnz cannot hold it (SURVEY.md section 4 quirk 6)
+    A.free()
+
+
 def test_config4_full_size_known_answers_and_checksum(engine):
     """BASELINE config 4 at full size against the analytic figures pinned in SURVEY.md section 8c and a
     size-independent property: sum(C) = sum_k colsum_k(A) * rowsum_k(A)."""

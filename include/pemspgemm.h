@@ -59,12 +59,16 @@ typedef enum pem_option {
      * SPA and NSPARSE hashing `B_tileCols > 512*32` (spgemm.cu:1142). */
     PEM_OPT_STEP1_PATH = 2,
     /* thread mapping of step 3 (and of step 2 for value 1).  Results are bit-identical.
-     * 0 (default) = automatic (currently always 2: it measured fastest on every workload, profiles/r01_summary.md)
-     * 1 = row-owner: sixteen lanes per C' tile, lane = tile row (steps 2 and 3)
-     * 2 = entry-owner: one thread per C nonzero (dense lane packing; hypersparse tiles)
-     * 3 = tile-owner: one warp per C' tile, lane = nonzero, pair data shared through shuffles
-     * 4 = row-owner with a dense 16x16 shared-memory accumulator per tile (dense tiles: stencils, FEM) */
-    PEM_OPT_OWNER = 3
+     * 0 (default) / 2 = entry-owner: one thread per C nonzero over the flat nonzero index space
+     * 1 = row-owner: sixteen lanes per C' tile, lane = tile row (steps 2 and 3; no pair kernel)
+     * 3 = tile-class kernel: a warp takes 32 consecutive C' tiles; small tiles get one thread each, the
+     *     others one warp each with their pairs' records staged in shared memory (or, for long pair
+     *     lists, found through step 2's hit blocks) */
+    PEM_OPT_OWNER = 3,
+    /* tuning of the tile-class kernel: a C' tile with at most SMALL_NNZ nonzeros (default 8) and at most
+     * SMALL_PAIRS pairs (default 64) is handled by one thread, any other tile by one warp */
+    PEM_OPT_S3_SMALL_NNZ = 4,
+    PEM_OPT_S3_SMALL_PAIRS = 5
 } pem_option;
 
 /* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are

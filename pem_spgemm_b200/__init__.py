@@ -26,6 +26,8 @@ STATUS = {0: "PEM_OK", -1: "PEM_ERR_CUDA", -2: "PEM_ERR_ARG", -3: "PEM_ERR_RANGE
 OPT_KEEP_EMPTY_TILES = 1
 OPT_STEP1_PATH = 2
 OPT_OWNER = 3
+OPT_S3_SMALL_NNZ = 4
+OPT_S3_SMALL_PAIRS = 5
 
 # pem_tiled_array / pem_result_array -> (index, dtype)
 T_ARRAYS = {

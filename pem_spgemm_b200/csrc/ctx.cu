@@ -151,8 +151,16 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
             ctx->opt_step1_path = (int)value;
             return PEM_OK;
         case PEM_OPT_OWNER:
-            if (value < 0 || value > 4) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0..4");
+            if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0..3");
             ctx->opt_owner = (int)value;
+            return PEM_OK;
+        case PEM_OPT_S3_SMALL_NNZ:
+            if (value < 0 || value > 256) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_S3_SMALL_NNZ must be 0..256");
+            ctx->opt_s3_small_e = (int)value;
+            return PEM_OK;
+        case PEM_OPT_S3_SMALL_PAIRS:
+            if (value < 0 || value > (1 << 20)) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_S3_SMALL_PAIRS must be 0..2^20");
+            ctx->opt_s3_small_np = (int)value;
             return PEM_OK;
     }
     return ctx->fail(PEM_ERR_ARG, "unknown option");

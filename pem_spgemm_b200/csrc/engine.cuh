@@ -31,7 +31,9 @@ struct pem_ctx {
     int64_t launches = 0;        // kernels of this library launched on the stream
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
-    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = auto, 1 = row-owner (registers), 2 = entry-owner, 3 = tile-owner, 4 = row-owner (shared-memory accumulator)
+    int opt_owner = 0;           // PEM_OPT_OWNER: 0 / 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel
+    int opt_s3_small_e = 8;      // PEM_OPT_S3_SMALL_NNZ: step 3 handles a tile with at most this many nonzeros ...
+    int opt_s3_small_np = 64;    // PEM_OPT_S3_SMALL_PAIRS: ... and at most this many pairs with one thread
     int sm_count = 148;
     int smem_optin = 227 * 1024; // max dynamic shared memory per block
     int64_t* h_scalars = nullptr; // pinned, PEM_NSCALARS entries: size read-backs
@@ -142,8 +144,7 @@ struct pem_result {
     int32_t tile_cols = 0;
     int64_t tiles = 0, pairs = 0, nnz = 0, tile_products = 0;
     int stage = 0;                    // 1, 2, 3 = last completed step
-    bool s3_tiles = false;            // step 3 runs a warp per C' tile instead of a thread per nonzero
-    bool s3_rows = false;             // step 3 runs sixteen lanes per C' tile with a dense shared-memory accumulator
+    bool s3_entries = false;          // step 3 runs the entry-owner kernel (PEM_OPT_OWNER = 2)
     int64_t* row_ptr = nullptr;       // [re-rb+1]
     int32_t* tile_row = nullptr;      // [tiles]
     int32_t* tile_col = nullptr;      // [tiles]
@@ -153,7 +154,7 @@ struct pem_result {
     int64_t* tile_nnz_ptr = nullptr;  // [tiles+1]
     uint8_t* row_col_idx = nullptr;   // [nnz], produced on demand (pem_result_make_rowcolidx)
     uint32_t* pair_hit = nullptr;     // [pairs] entry-owner variant: (C rows hit << 16) | C columns hit by the pair
-    int32_t* blk_tile = nullptr;      // entry-owner variant: first tile of each 256-entry step-3 block
+    int32_t* blk_tile = nullptr;      // entry-owner variant: first tile of each 128-entry step-3 block
     int32_t* pair_blk = nullptr;      // first tile of each 256-pair step-2 block (optional by-product of step 1)
     double* vals = nullptr;           // [nnz]
 };

@@ -4,11 +4,7 @@
 //   step 2  per-tile bitmask symbolic: C tile masks, per-tile nnz, scan (rowColIdx on request only).
 //           Replaces pem_spgemm_step2_compute_CMasksAndOffsets (:499-550) and ..._CrowColIdx
 //           (:552-591).  Default mapping: one thread per (A tile, B tile) pair (k_step2_pairs).
-//   step 3  numeric: ascending-k fma chain per C nonzero, C written exactly once, no floating-point
-//           atomics.  Replaces pem_spgemm_step3_accumulate (:593-661).  Default mapping: one thread
-//           per C nonzero (k_step3_entries); three more mappings are selectable (PEM_OPT_OWNER) and
-//           bit-identical: row-owner in registers (first block below), tile-owner, row-owner with a
-//           shared-memory accumulator.
+//   step 3  numeric: lives in step3.cu.
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -102,111 +98,13 @@ k_rowcolidx(int64_t n_tiles, const uint16_t* __restrict__ Cmasks, const int64_t*
     for (int i = 0; i < nb; ++i) dst[i] = (uint8_t)(buf >> (8 * i));
 }
 
-// step 3 (row-owner): numeric.  Lane r accumulates its C row in FOUR REGISTERS: the nonzeros of
-// the row are numbered by rank inside Cmask[r] and handled four ranks per pass (nearly every row of
-// a sparse product has <= 4 nonzeros per tile, i.e. one pass; a fully dense row takes four).  No
-// shared memory, so the kernel keeps full occupancy and the whole L1.  For every pair (the next
-// pair's ids and A row mask are prefetched), every k in Amask[r] (ascending; the A values of the row
-// are consecutive), every c in Bmask[k] that belongs to the pass (ascending):
-//     acc[rank(c)] = fma(a, b, acc[rank(c)])
-// Replaces pem_spgemm_step3_accumulate (spgemm.cu:593-661): no global read-modify-write per
-// product, C written once, sequentially per row.
-constexpr int S3_THREADS = 256;
-constexpr int S3_NACC = 4;
-
-__global__ void __launch_bounds__(S3_THREADS)
-k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-                const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
-                const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
-                const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
-                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
-                const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
-                double* __restrict__ C_vals)
-{
-    const int tid = threadIdx.x;
-    const int64_t t = ((int64_t)blockIdx.x * S3_THREADS + tid) >> 4;
-    const unsigned r = tid & 15u;
-    if (t >= n_tiles) return;                       // whole 16-lane groups leave together
-    const unsigned grp = 0xFFFFu << (tid & 16);
-    const unsigned cm = Cmasks[t * 16 + r];
-    // offset of row r inside the tile: exclusive scan of the row popcounts over the 16 lanes
-    const int pc = __popc(cm);
-    int incl = pc;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        const int v = __shfl_up_sync(grp, incl, o, 16);
-        if ((int)r >= o) incl += v;
-    }
-    if (cm == 0) return;                            // nothing lands in this row
-    const int64_t ps = pair_ptr[t];
-    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
-    const int2* __restrict__ pl = pairs + ps;
-    double* __restrict__ out = C_vals + c_tile_nnz_ptr[t] + (incl - pc);
-    unsigned rest = cm;                             // columns not yet produced
-    for (int lo = 0; lo < pc; lo += S3_NACC) {
-        // the (up to) four lowest remaining columns form this pass
-        unsigned pm = 0;
-#pragma unroll
-        for (int j = 0; j < S3_NACC; ++j) {
-            const unsigned low = rest & (0u - rest);
-            pm |= low;
-            rest ^= low;
-        }
-        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-        int2 ab_n = pl[0];
-        unsigned am_n = A_masks[(unsigned)ab_n.x * 16u + r];
-        for (unsigned i = 0; i < np; ++i) {
-            const int2 ab = ab_n;
-            unsigned am = am_n;
-            if (i + 1 < np) {                       // prefetch the next pair
-                ab_n = pl[i + 1];
-                am_n = A_masks[(unsigned)ab_n.x * 16u + r];
-            }
-            if (am) {
-                const unsigned ib = (unsigned)ab.y * 16u;
-                const double* __restrict__ ap = A_vals + (A_off[ab.x] + A_rowptr[(unsigned)ab.x * 16u + r]);
-                const double* __restrict__ bbase = B_vals + B_off[ab.y];
-                do {
-                    const unsigned k = __ffs(am) - 1;
-                    am &= am - 1;
-                    const unsigned bm = B_masks[ib + k];
-                    unsigned hit = bm & pm;
-                    if (hit) {
-                        const double a = *ap;
-                        const double* __restrict__ bp = bbase + B_rowptr[ib + k];
-                        do {
-                            const unsigned low = hit & (0u - hit);
-                            hit ^= low;
-                            const double b = bp[__popc(bm & (low - 1u))];
-                            const int idx = __popc(pm & (low - 1u));
-                            const double v0 = fma(a, b, acc0), v1 = fma(a, b, acc1), v2 = fma(a, b, acc2), v3 = fma(a, b, acc3);
-                            acc0 = idx == 0 ? v0 : acc0;
-                            acc1 = idx == 1 ? v1 : acc1;
-                            acc2 = idx == 2 ? v2 : acc2;
-                            acc3 = idx == 3 ? v3 : acc3;
-                        } while (hit);
-                    }
-                    ++ap;
-                } while (am);
-            }
-        }
-        const int cnt = min(S3_NACC, pc - lo);
-        out[0] = acc0;
-        if (cnt > 1) out[1] = acc1;
-        if (cnt > 2) out[2] = acc2;
-        if (cnt > 3) out[3] = acc3;
-        out += S3_NACC;
-    }
-}
-
 // =========================================================================================
 // Default mapping of steps 2 and 3.
 //   step 2: one thread per (A tile, B tile) PAIR.  The C tile mask is an OR over the tile's pairs,
 //           and OR is associative, so the pairs are the unit of work: no thread waits on a long
 //           pair list (hub tiles own thousands of pairs), every lane of every warp owns one 16x16
 //           boolean product.
-//   step 3: one thread per C NONZERO ("entry-owner", k_step3_entries) when C's tiles are sparse,
-//           one warp per C' tile (k_step3_tiles) when they are dense.
+//   step 3: step3.cu.
 // =========================================================================================
 
 // first tile of every PEM_PAIR_BLOCK-pair step-2 block (every C' tile owns >= 1 pair, so a block overlaps
@@ -368,287 +266,6 @@ struct TileNnz {
     }
 };
 
-// first tile of every entry-owner step-3 block (a tile of up to 256 nonzeros can cover two block
-// boundaries).  128 nonzeros per block measured best (256: +4.5 % on config 4, 64: +1 %).
-constexpr int S3E_ENTRIES = 128;
-__global__ void __launch_bounds__(256)
-k_block_tiles(int64_t n_tiles, const int64_t* __restrict__ c_tile_nnz_ptr, int32_t* __restrict__ blk_tile)
-{
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    const int64_t off = c_tile_nnz_ptr[t], end = c_tile_nnz_ptr[t + 1];
-    if (end > off) {
-        for (int64_t bnd = (off + S3E_ENTRIES - 1) / S3E_ENTRIES * S3E_ENTRIES; bnd < end; bnd += S3E_ENTRIES)
-            blk_tile[bnd / S3E_ENTRIES] = (int32_t)t;
-    }
-}
-
-// step 3 (entry-owner): the block covers S3E_ENTRIES consecutive nonzeros; the offsets of the
-// tiles it overlaps are staged in shared memory and each thread finds its tile by binary search
-// there.  A thread then walks its tile's pair list in order, skipping pairs whose hit word rules its
-// (r, c) out, and for each remaining pair
-//   m = Amask[r] & BmaskT[c];  for each k in m (ascending):  acc = fma(a_rk, b_kc, acc)
-// Same product order as the reference (:648-656) and as the host oracle; C is written once.
-constexpr int S3E_TMAX = 512;
-
-__global__ void __launch_bounds__(S3E_ENTRIES, 16)
-k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
-                const int64_t* __restrict__ c_tile_nnz_ptr, const uint32_t* __restrict__ Cmasks32,
-                const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-                const uint32_t* __restrict__ hit_t,
-                const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
-                const uint32_t* __restrict__ A_row_rec,
-                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals_t,
-                const uint32_t* __restrict__ B_col_rec, double* __restrict__ C_vals)
-{
-    __shared__ int s_off[S3E_TMAX];
-    const int tid = threadIdx.x;
-    const int64_t n0 = (int64_t)blockIdx.x * S3E_ENTRIES;
-    const int64_t t0 = blk_tile[blockIdx.x];
-    const int64_t t1 = (n0 + S3E_ENTRIES < nnz) ? (int64_t)blk_tile[blockIdx.x + 1] : n_tiles - 1;
-    const int64_t span = t1 - t0 + 1;
-    const bool staged = span <= S3E_TMAX;
-    if (staged)
-        for (int i = tid; i < (int)span; i += S3E_ENTRIES) s_off[i] = (int)(c_tile_nnz_ptr[t0 + i] - n0);
-    __syncthreads();
-    const int64_t n = n0 + tid;
-    if (n >= nnz) return;
-    int64_t t;
-    int e;                                          // rank of this nonzero inside its tile
-    if (staged) {                                   // last i with s_off[i] <= tid
-        int lo = 0, hi = (int)span - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_off[mid] <= tid) lo = mid; else hi = mid - 1;
-        }
-        t = t0 + lo;
-        e = tid - s_off[lo];
-    } else {                                        // many empty tiles in range (keep_empty mode)
-        int64_t lo = t0, hi = t1;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi + 1) >> 1;
-            if (c_tile_nnz_ptr[mid] <= n) lo = mid; else hi = mid - 1;
-        }
-        t = lo;
-        e = (int)(n - c_tile_nnz_ptr[t]);
-    }
-    // (r, c) = position of the e-th set bit of the tile's 256-bit mask (word w = rows 2w, 2w+1), which
-    // is what Ctiles_rowColIdx[n] would hold (spgemm.cu:552-591) without materialising that array
-    unsigned r, c;
-    {
-        const uint4* m4 = reinterpret_cast<const uint4*>(Cmasks32 + (size_t)t * 8);
-        const uint4 x = m4[0], y = m4[1];
-        const unsigned w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-        unsigned sel = 0, wi = 0;
-        int rem = e;
-        bool done = false;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int pc = __popc(w[i]);
-            const bool here = !done && rem < pc;
-            sel = here ? w[i] : sel;
-            wi = here ? (unsigned)i : wi;
-            done = done || here;
-            rem -= done ? 0 : pc;
-        }
-        unsigned b = 0;                             // position of the rem-th set bit of sel: 5 halving steps
-#pragma unroll
-        for (int width = 16; width > 0; width >>= 1) {
-            const int pc = __popc(sel & (((1u << width) - 1u) << b));
-            const bool up = rem >= pc;
-            rem -= up ? pc : 0;
-            b += up ? (unsigned)width : 0u;
-        }
-        r = 2u * wi + (b >> 4);
-        c = b & 15u;
-    }
-    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
-    double acc = 0.0;
-    for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
-        // pairs of this 32-pair block that touch C row r and C column c
-        unsigned w = hit_t[base + 16 + r] & hit_t[base + c];
-        if (base < ps) w &= 0xFFFFFFFFu << (unsigned)(ps - base);
-        if (base + 32 > pe) w &= 0xFFFFFFFFu >> (unsigned)(base + 32 - pe);
-        while (w) {
-            const int64_t i = base + (__ffs(w) - 1);
-            w &= w - 1;
-            const int2 ab = pairs[i];
-            // one record per A tile row / B tile column: mask | offset of its first value << 16
-            const unsigned ar = A_row_rec[(unsigned)ab.x * 16u + r];
-            const unsigned bc = B_col_rec[(unsigned)ab.y * 16u + c];
-            const unsigned ao = A_off[ab.x], bo = B_off[ab.y];      // issued with the records, not after the mask test
-            unsigned m = ar & bc & 0xFFFFu;
-            if (m) {
-                const double* __restrict__ av = A_vals + (ao + (ar >> 16));        // row r of the A tile
-                const double* __restrict__ bv = B_vals_t + (bo + (bc >> 16));      // column c of the B tile
-                do {
-                    const unsigned low = m & (0u - m);
-                    m ^= low;
-                    const unsigned lt = low - 1u;                // lt < 2^16: the offset bits drop out of the ranks
-                    acc = fma(av[__popc(ar & lt)], bv[__popc(bc & lt)], acc);
-                } while (m);
-            }
-        }
-    }
-    C_vals[n] = acc;
-}
-
-// step 3 (tile-owner): ONE WARP PER C' TILE, lane = C nonzero (32 per pass).  What the entry-owner
-// kernel fetches once per entry and pair - the pair's ids, the A row masks / row pointers, the B row
-// and column masks / row pointers, the two value offsets - is fetched once per WARP and pair here
-// (sixteen lanes load one 16-entry array each, coalesced) and handed to the entry's lane with
-// shuffles; the per-product index arithmetic (rank of k in the A row, rank of c in B row k) also
-// runs on shuffled registers.  Pays off when C tiles are dense (FEM / stencil matrices: ~30
-// nonzeros per tile); same ascending-k fma order as every other variant, so the bits agree.
-constexpr int S3W_THREADS = 256;
-__global__ void __launch_bounds__(S3W_THREADS)
-k_step3_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-              const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
-              const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
-              const uint16_t* __restrict__ A_masks, const uint8_t* __restrict__ A_rowptr,
-              const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals,
-              const uint16_t* __restrict__ B_masks, const uint8_t* __restrict__ B_rowptr,
-              const uint16_t* __restrict__ B_masks_t, double* __restrict__ C_vals)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, h = lane & 15;
-    const int64_t t = ((int64_t)blockIdx.x * S3W_THREADS + threadIdx.x) >> 5;
-    if (t >= n_tiles) return;                       // whole warps leave together
-    const unsigned cm = Cmasks[t * 16 + h];
-    const int pc = __popc(cm);
-    int incl = pc;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, o, 16);
-        if (h >= o) incl += v;
-    }
-    const int crp = incl - pc;                      // first entry of C row h inside the tile
-    const int E = __shfl_sync(FULL, incl, 15);
-    if (E == 0) return;
-    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
-    double* __restrict__ out = C_vals + c_tile_nnz_ptr[t];
-    for (int e0 = 0; e0 < E; e0 += 32) {
-        const int e = e0 + lane;
-        const bool active = e < E;
-        // (r, c) of entry e: r = last row whose first entry is <= e, c = the (e - first)th bit of the row mask
-        int r = 0;
-#pragma unroll
-        for (int step = 8; step > 0; step >>= 1) {
-            const int v = __shfl_sync(FULL, crp, r + step);
-            if (v <= e) r += step;
-        }
-        const unsigned cmr = __shfl_sync(FULL, cm, r);
-        const int first = __shfl_sync(FULL, crp, r);
-        const unsigned c = active ? __fns(cmr, 0, e - first + 1) : 0u;
-        const unsigned below_c = (1u << c) - 1u;
-        double acc = 0.0;
-        int2 ab = pairs[ps];
-        for (int64_t i = ps; i < pe; ++i) {
-            const unsigned ia = (unsigned)ab.x * 16u, ib = (unsigned)ab.y * 16u;
-            const unsigned a_pack = A_masks[ia + h] | ((unsigned)A_rowptr[ia + h] << 16);
-            const unsigned b_pack = B_masks[ib + h] | ((unsigned)B_rowptr[ib + h] << 16);
-            const unsigned bt_h = B_masks_t[ib + h];
-            const double* __restrict__ av = A_vals + A_off[ab.x];
-            const double* __restrict__ bv = B_vals + B_off[ab.y];
-            if (i + 1 < pe) ab = pairs[i + 1];      // next pair's ids while this one is consumed
-            const unsigned ar = __shfl_sync(FULL, a_pack, r);
-            const unsigned am = ar & 0xFFFFu;
-            const unsigned bt = __shfl_sync(FULL, bt_h, c);      // outside the select: every lane must take part
-            unsigned m = active ? (am & bt) : 0u;
-            while (__any_sync(FULL, m != 0)) {
-                const unsigned k = m ? __ffs(m) - 1 : 0u;
-                const unsigned bk = __shfl_sync(FULL, b_pack, k);
-                if (m) {
-                    const unsigned ao = (ar >> 16) + __popc(am & ((1u << k) - 1u));
-                    const unsigned bo = (bk >> 16) + __popc(bk & below_c);   // below_c < 2^16: the row-pointer bits drop out
-                    acc = fma(av[ao], bv[bo], acc);
-                    m &= m - 1;
-                }
-            }
-        }
-        if (active) out[e] = acc;
-    }
-}
-
-// step 3 (row-owner, dense accumulator): SIXTEEN LANES PER C' TILE, lane = tile row r, with the row's 16
-// possible entries accumulated in shared memory.  The lane runs Gustavson inside the tile pair:
-//     for k in Arow[r] (ascending; the row's values are consecutive):  a = *ap++
-//         for c in Brow[k] (ascending; consecutive values):            acc[r][c] = fma(a, *bp++, acc[r][c])
-// so it only ever touches products that exist - no per-entry "does this pair feed me" test - and
-// every product lands on a structural nonzero of C by construction of the mask.  Each C entry still
-// receives its products in ascending (pair, k), i.e. the oracle's order: same bits as every other
-// variant.  Rows are padded to 17 doubles so the 16 lanes of a tile hit distinct banks unless their
-// r + c coincide.  Used when C's tiles are dense (stencil / FEM matrices: ~30 nonzeros per tile), where
-// the entry-owner kernel spends most of its instructions on (entry, pair) combinations without products.
-constexpr int S3R_THREADS = 256;
-__global__ void __launch_bounds__(S3R_THREADS)
-k_step3_rows(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
-             const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
-             const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals, const uint32_t* __restrict__ A_row_rec,
-             const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals, const uint32_t* __restrict__ B_row_rec,
-             double* __restrict__ C_vals)
-{
-    __shared__ double s_acc[S3R_THREADS / 16][16 * 17];
-    const int tid = threadIdx.x;
-    const int64_t t = ((int64_t)blockIdx.x * S3R_THREADS + tid) >> 4;
-    const unsigned r = tid & 15u;
-    if (t >= n_tiles) return;                       // whole 16-lane groups leave together
-    const unsigned grp = 0xFFFFu << (tid & 16);
-    const unsigned cm = Cmasks[t * 16 + r];
-    const int pc = __popc(cm);
-    int incl = pc;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        const int v = __shfl_up_sync(grp, incl, o, 16);
-        if ((int)r >= o) incl += v;
-    }
-    if (cm == 0) return;                            // nothing lands in this row
-    double* __restrict__ acc = &s_acc[tid >> 4][r * 17];
-    {
-        unsigned z = cm;
-        while (z) {
-            acc[__ffs(z) - 1] = 0.0;
-            z &= z - 1;
-        }
-    }
-    const int64_t ps = pair_ptr[t], pe = pair_ptr[t + 1];
-    int2 ab = pairs[ps];
-    unsigned ar = A_row_rec[(unsigned)ab.x * 16u + r];
-    for (int64_t i = ps; i < pe; ++i) {
-        const int2 cur = ab;
-        unsigned am = ar & 0xFFFFu;
-        const unsigned a_first = ar >> 16;
-        if (i + 1 < pe) {                           // next pair's ids and A row record while this one is consumed
-            ab = pairs[i + 1];
-            ar = A_row_rec[(unsigned)ab.x * 16u + r];
-        }
-        if (am) {
-            const double* __restrict__ ap = A_vals + (A_off[cur.x] + a_first);
-            const uint32_t* __restrict__ brec = B_row_rec + (size_t)(unsigned)cur.y * 16u;
-            const double* __restrict__ bvals = B_vals + B_off[cur.y];
-            do {
-                const unsigned k = __ffs(am) - 1;
-                am &= am - 1;
-                const double a = *ap++;
-                const unsigned br = brec[k];
-                unsigned bm = br & 0xFFFFu;
-                const double* __restrict__ bp = bvals + (br >> 16);
-                while (bm) {
-                    const unsigned c = __ffs(bm) - 1;
-                    bm &= bm - 1;
-                    acc[c] = fma(a, *bp++, acc[c]);
-                }
-            } while (am);
-        }
-    }
-    double* __restrict__ out = C_vals + c_tile_nnz_ptr[t] + (incl - pc);
-    unsigned m = cm;
-    while (m) {
-        *out++ = acc[__ffs(m) - 1];
-        m &= m - 1;
-    }
-}
-
 __global__ void k_set_last_i64(int64_t* p, int64_t idx, int64_t v) { p[idx] = v; }
 
 }  // namespace
@@ -721,67 +338,8 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     C->nnz = ctx->h_scalars[0];
     C->stage = 2;
-    // step-3 mapping: a thread per nonzero by default; a warp per C' tile on request
-    // (measured on B200, profiles/: the entry-owner kernel wins on every BASELINE config, including the
-    // stencil matrix with ~30 nonzeros per C tile, so the tile-owner kernel is opt-in)
-    C->s3_tiles = ctx->opt_owner == 3;
-    C->s3_rows = ctx->opt_owner == 4;     // measured 20.8 ms against 13.3 ms on config 4: opt-in as well
-    if (!rows_variant && !C->s3_tiles && !C->s3_rows) {   // what the entry-owner step 3 reads: first tile of every 256-nonzero block
-        const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
-        PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
-        if (C->tiles > 0) {
-            k_block_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->tile_nnz_ptr, C->blk_tile);
-            PEM_LAUNCHED();
-        }
-    }
-    return PEM_OK;
-}
-
-int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
-{
-    if (!ctx || !A || !B || !C) return PEM_ERR_ARG;
-    if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
-    PEM_CK(cudaSetDevice(ctx->device));
-    PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
-    if (C->nnz > 0 && C->s3_rows) {         // views are cached on the handles after the first product
-        PEM_TRY(pem_tiled_build_views(ctx, A, true, false));
-        PEM_TRY(pem_tiled_build_views(ctx, B, true, false));
-    }
-    KT_BEGIN(KT_NUMERIC);
-    if (C->nnz > 0 && C->s3_rows) {
-        const int64_t nblk = (C->tiles * 16 + S3R_THREADS - 1) / S3R_THREADS;
-        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^35 tiles");
-        k_step3_rows<<<(unsigned)nblk, S3R_THREADS, 0, ctx->stream>>>(
-            C->tiles, C->pair_ptr, C->pair_list, C->masks, C->tile_nnz_ptr,
-            A->tile_nnz_ptr, A->vals, A->row_rec, B->tile_nnz_ptr, B->vals, B->row_rec, C->vals);
-        PEM_LAUNCHED();
-    } else if (C->nnz > 0 && C->s3_tiles) {
-        const int64_t nblk = (C->tiles * 32 + S3W_THREADS - 1) / S3W_THREADS;
-        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^34 tiles");
-        k_step3_tiles<<<(unsigned)nblk, S3W_THREADS, 0, ctx->stream>>>(
-            C->tiles, C->pair_ptr, C->pair_list, C->masks, C->tile_nnz_ptr,
-            A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr,
-            B->masks_t, C->vals);
-        PEM_LAUNCHED();
-    } else if (C->nnz > 0 && C->pair_hit) {      // entry-owner variant (step 2 prepared its inputs)
-        PEM_TRY(pem_tiled_build_views(ctx, A, true, false));   // cached on the handles after the first product
-        PEM_TRY(pem_tiled_build_views(ctx, B, false, true));
-        const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
-        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^39 nonzeros");
-        k_step3_entries<<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(
-            C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, reinterpret_cast<const uint32_t*>(C->masks), C->pair_ptr, C->pair_list, C->pair_hit,
-            A->tile_nnz_ptr, A->vals, A->row_rec, B->tile_nnz_ptr, B->vals_t, B->col_rec, C->vals);
-        PEM_LAUNCHED();
-    } else if (C->tiles > 0) {
-        const int64_t nblk = (C->tiles * 16 + S3_THREADS - 1) / S3_THREADS;
-        if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^35 tiles");
-        k_step3_numeric<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(
-            C->tiles, C->pair_ptr, C->pair_list, C->masks, C->tile_nnz_ptr,
-            A->tile_nnz_ptr, A->vals, A->masks, A->row_ptr, B->tile_nnz_ptr, B->vals, B->masks, B->row_ptr, C->vals);
-        PEM_LAUNCHED();
-    }
-    KT_END(KT_NUMERIC);
-    C->stage = 3;
+    // step-3 mapping (step3.cu): the entry-owner kernel unless the tile-class kernel is asked for
+    C->s3_entries = ctx->opt_owner != 3;
     return PEM_OK;
 }
 

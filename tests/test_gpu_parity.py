@@ -54,14 +54,14 @@ def test_conversion_matches_tile_oracle(engine, shape, nnz, seed, transpose):
 
 
 def test_dense_blocks_all_step3_variants(engine):
-    """Fully dense 16x16 tiles (256 nonzeros per C tile: eight passes of the tile-owner kernel,
-    a whole block of the entry-owner one) and a ragged dense matrix."""
+    """Fully dense 16x16 tiles (256 nonzeros per C tile: eight passes of a warp in the tile-class kernel,
+    two whole blocks of the entry-owner one) and a ragged dense matrix."""
     for n in (32, 40):
         I, J = np.divmod(np.arange(n * n, dtype=np.int32), n)
         V = np.random.default_rng(n).uniform(-1, 1, n * n)
         _, _, oC = host.spgemm_from_coo(n, n, I, J, V, False)
         A = engine.convert_coo(n, n, I, J, V)
-        for owner in (0, 1, 2, 3, 4):
+        for owner in (0, 1, 2, 3):
             engine.set_option(pem.OPT_OWNER, owner)
             try:
                 C = engine.spgemm(A, A)
@@ -236,10 +236,10 @@ def test_device_pointer_input_and_pool_reuse(engine):
     A.free()
 
 
-@pytest.mark.parametrize("owner", [1, 2, 3, 4])
+@pytest.mark.parametrize("owner", [1, 2, 3])
 @pytest.mark.parametrize("k", [1, 2, 3, 4])
 def test_owner_variants_are_bit_identical(engine, k, owner):
-    """PEM_OPT_OWNER = 1 (row-owner), 2 (entry-owner), 3 (tile-owner), 4 (row-owner, shared accumulator) must give the same bits as
+    """PEM_OPT_OWNER = 1 (row-owner), 2 (entry-owner), 3 (tile-class kernel) must give the same bits as
     the automatic choice and as the oracle."""
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
     A = engine.convert_coo(rows, cols, I, J, V)
@@ -257,6 +257,35 @@ def test_owner_variants_are_bit_identical(engine, k, owner):
     _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
     _assert_same_C(C1, oC)
     C0.free(); C1.free(); A.free(); B.free()
+
+
+@pytest.mark.parametrize("small_e,small_np", [(0, 0), (256, 1 << 20), (256, 1), (2, 4), (8, 0)])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_step3_tile_classes_are_bit_identical(engine, k, small_e, small_np):
+    """The tile-class kernel of step 3 with its thresholds pushed to the extremes, so that every tile goes
+    through the warp mappings (staged records / hit blocks), or every tile through the one-thread mapping
+    (single-pair walk / hit blocks): same bits as the oracle whatever the class."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.transpose(A) if tb else A
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    engine.set_option(pem.OPT_S3_SMALL_NNZ, small_e)
+    engine.set_option(pem.OPT_S3_SMALL_PAIRS, small_np)
+    engine.set_option(pem.OPT_OWNER, 3)
+    try:
+        for keep in (0, 1):
+            engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep)
+            C = engine.spgemm(A, B)
+            _assert_same_C(C, oC)
+            C.free()
+    finally:
+        engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+        engine.set_option(pem.OPT_OWNER, 0)
+        engine.set_option(pem.OPT_S3_SMALL_NNZ, 8)
+        engine.set_option(pem.OPT_S3_SMALL_PAIRS, 64)
+    if B is not A:
+        B.free()
+    A.free()
 
 
 @pytest.mark.parametrize("esc", [3, 4])
@@ -461,7 +490,7 @@ def test_fuzz_all_variants_against_oracle(engine):
         A = engine.convert_coo(rows, cols, I, J, V)
         B = engine.transpose(A) if aat else A
         path = (1, 3, 4)[case % 3]
-        owner = (2, 4, 1, 3)[case % 4]
+        owner = (2, 0, 1, 3)[case % 4]
         keep = case % 2
         engine.set_option(pem.OPT_STEP1_PATH, path)
         engine.set_option(pem.OPT_OWNER, owner)

@@ -15,6 +15,7 @@ ap.add_argument("--small", action="store_true")
 ap.add_argument("--panels", type=int, default=1, help="multiply in this many sequential tile-row panels (results freed panel by panel)")
 ap.add_argument("--owner", type=int, default=0)
 ap.add_argument("--step1", type=int, default=0)
+ap.add_argument("--sweep", default="", help="comma list of owner:small_nnz:small_pairs variants timed on the same operands, e.g. 0:8:64,0:4:64,2:8:64")
 a = ap.parse_args()
 ctx = pem.Context(0)
 ctx.set_option(pem.OPT_KEEP_EMPTY_TILES, a.keep_empty)
@@ -30,6 +31,18 @@ for k in a.configs:
     flop = ctx.count_flop(A, B)
     best = None
     bounds = ctx.partition_panels(A, B, a.panels)
+    for var in [v for v in a.sweep.split(",") if v]:
+        ow, se, sp = (int(x) for x in var.split(":"))
+        ctx.set_option(pem.OPT_OWNER, ow); ctx.set_option(pem.OPT_S3_SMALL_NNZ, se); ctx.set_option(pem.OPT_S3_SMALL_PAIRS, sp)
+        bt = None
+        for r in range(a.reps):
+            t = pem.Times()
+            C = ctx.spgemm(A, B, times=t)
+            C.free()
+            if bt is None or t.step3_ms < bt.step3_ms:
+                bt = t; bk = ctx.kernel_ms()
+        print(f"   sweep owner {ow} small_nnz {se} small_pairs {sp}: step1 {bt.step1_ms:.3f} step2 {bt.step2_ms:.3f} step3 {bt.step3_ms:.3f} total {bt.total_ms:.3f} | numeric kernel {bk['step3_numeric']:.3f}", flush=True)
+    ctx.set_option(pem.OPT_OWNER, a.owner); ctx.set_option(pem.OPT_S3_SMALL_NNZ, 8); ctx.set_option(pem.OPT_S3_SMALL_PAIRS, 64)
     for r in range(a.reps):
         t = pem.Times()
         tot = dict(tiles=0, pairs=0, nnz=0, tile_products=0)

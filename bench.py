@@ -139,8 +139,10 @@ def load_workload(k):
 
 
 def oracle_cpu(rows, cols, I, J, V, tb):
-    """The host oracle timed on this box's cores (reported baseline, not the target)."""
+    """The host oracle timed on this box's cores (reported baseline, not the target).  All host cores are
+    asked for explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers."""
     from oracle import host   # cpu_baseline leg: one of the places allowed to run oracle/
+    host.set_threads(os.cpu_count() or 1)
     A = host.coo_to_csr(rows, cols, I, J, V)
     B = host.transpose(A) if tb else A
     flop = host.flop(A, B)
@@ -149,55 +151,73 @@ def oracle_cpu(rows, cols, I, J, V, tb):
     return flop, tm["seconds"], tm["threads"]
 
 
+def static_config(k, tb):
+    """The `config` object both arms print (same keys, same values: the driver compares them)."""
+    return {"workload": CONFIG_TEXT[k], "product": "A*A^T" if tb else "A^2"}
+
+
 def run_reference(args, rank):
-    """--impl reference: the UNMODIFIED reference (oracle/_ref/pemspgemm_ref = /root/reference's
-    spgemm.cu compiled for sm_100 against shim headers) through its own CLI on one B200; if that
-    binary is missing or fails on this input, the host oracle port on the box's cores."""
+    """--impl reference: the UNMODIFIED reference source (/root/reference/spgemm.cu compiled against shim
+    headers, oracle/Makefile) through its own CLI on one B200.  oracle/_ref/pemspgemm_ref61 is built with the
+    reference's own virtual architecture (compute_61 PTX, /root/reference/Makefile:13), the only rebuild whose
+    NSPARSE step 1 terminates on sm_100 (profiles/r02_reference_runs.md); pemspgemm_ref (compute_100 PTX) is
+    tried for inputs that stay on the SPA path.  If no binary is present or both fail on this input (config 2:
+    the reference aborts inside thrust; config 5: int32 sizes), the host oracle port on all host cores."""
     if rank != 0:
         return
     import pem_spgemm_b200 as pem
     name, tb, rows, cols, I, J, V = load_workload(args.config)
     line = {"impl": "reference", "metric": "spgemm_gflops", "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": CONFIG_TEXT[args.config]}}
-    ref = os.path.join(ROOT, "oracle", "_ref", "pemspgemm_ref")
-    done = False
+            "dtype": "f64", "data": "synthetic", "config": static_config(args.config, tb)}
     b_tile_cols = ((rows if tb else cols) + 15) // 16
-    if b_tile_cols > 512 * 32:
-        # /root/reference/spgemm.cu:1142 sends this input down its NSPARSE hash path, which does not
-        # terminate on sm_100 (two B200 runs, 900 s and 60 s time-outs inside "step1 using NSPARSE";
-        # profiles/r01_reference_runs.md).  Not launched: a hung kernel would only burn the box.
-        line["reference_failure"] = (f"reference rebuilt for sm_100 hangs in its NSPARSE step 1 on inputs with "
-                                     f"> 16384 B tile columns (this one: {b_tile_cols}); host oracle port timed instead")
-    elif os.path.exists(ref):
-        work = f"/tmp/pem_ref_{os.getpid()}"
+    nsparse = b_tile_cols > 512 * 32           # /root/reference/spgemm.cu:1142
+    bins = ["pemspgemm_ref61"] + ([] if nsparse else ["pemspgemm_ref"])
+    failures, done = [], False
+    work = f"/tmp/pem_ref_{os.getpid()}"
+    mtx = os.path.join(work, f"{name}.mtx")
+    for b in bins:
+        ref = os.path.join(ROOT, "oracle", "_ref", b)
+        if not os.path.exists(ref):
+            failures.append(f"{b}: not built")
+            continue
+        if args.config == 5:
+            failures.append(f"{b}: not launched, nnz(C) = 2.5e9 exceeds the reference's int32 sizes (spgemm.cu:727-728)")
+            continue
         os.makedirs(work, exist_ok=True)
-        mtx = os.path.join(work, f"{name}.mtx")
-        pem.mtx_write(mtx, rows, cols, I, J, V)
-        cmd = [ref, mtx, "0"] + (["1"] if tb else [])
+        if not os.path.exists(mtx):
+            pem.mtx_write(mtx, rows, cols, I, J, V)
+        csv = os.path.join(work, "pemspgemm_benchmark_result.csv")
+        if os.path.exists(csv):
+            os.remove(csv)
         try:
             t0 = time.time()
-            out = subprocess.run(cmd, cwd=work, capture_output=True, text=True, timeout=600)
+            out = subprocess.run([ref, mtx, "0"] + (["1"] if tb else []), cwd=work, capture_output=True, text=True, timeout=420)
             wall = time.time() - t0
-            row = open(os.path.join(work, "pemspgemm_benchmark_result.csv")).read().strip().splitlines()[-1].split(",")
+            if out.returncode != 0:
+                failures.append(f"{b}: rc={out.returncode} {out.stderr.strip()[-200:]}")
+                continue
+            row = open(csv).read().strip().splitlines()[-1].split(",")
             flop, c_nnz, t_ms, gf = int(row[1]), int(row[2]), float(row[10]), float(row[13])
-            if out.returncode == 0 and t_ms > 0 and c_nnz > 0:
-                line.update({"value": gf, "ms_per_step": t_ms, "steps": 10, "warmup": 1,
-                             "reference_csv": {"flop": flop, "C_nnz": c_nnz, "step1_ms": float(row[7]),
-                                               "step2_ms": float(row[8]), "step3_ms": float(row[9]),
-                                               "kernel_ms": float(row[11]), "malloc_ms": float(row[12])},
-                             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": 0, "kind": "reference",
-                                              "sample": "reference CUDA source rebuilt for sm_100, its own CLI: "
-                                                        "1 warm-up + 10 timed iterations on 1 B200 (it has no CPU path); "
-                                                        f"whole process {wall:.1f}s"},
-                             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-                done = True
-            else:
-                line["reference_failure"] = f"rc={out.returncode} time_ms={t_ms} C_nnz={c_nnz}: {out.stderr[-300:]}"
-        except Exception as e:  # crash, timeout, no CSV
-            line["reference_failure"] = f"{type(e).__name__}: {e}"[:400]
-    else:
-        line["reference_failure"] = "oracle/_ref/pemspgemm_ref not built"
+            if not (t_ms > 0 and c_nnz > 0):
+                failures.append(f"{b}: time_ms={t_ms} C_nnz={c_nnz}")
+                continue
+            line.update({"value": gf, "ms_per_step": t_ms, "steps": 10, "warmup": 1,
+                         "reference_binary": b,
+                         "reference_csv": {"flop": flop, "C_nnz": c_nnz, "step1_ms": float(row[7]),
+                                           "step2_ms": float(row[8]), "step3_ms": float(row[9]),
+                                           "kernel_ms": float(row[11]), "malloc_ms": float(row[12])},
+                         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": 0, "kind": "reference",
+                                          "sample": f"reference CUDA source rebuilt for sm_100 ({b}), its own CLI: "
+                                                    "1 warm-up + 10 timed iterations of the full workload on 1 B200 (it has no CPU path); "
+                                                    f"whole process {wall:.1f}s"},
+                         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            done = True
+            break
+        except Exception as e:  # timeout, no CSV
+            failures.append(f"{b}: {type(e).__name__}: {e}"[:300])
+    if failures:
+        line["reference_failure"] = "; ".join(failures)
     if not done:
         flop, secs, thr = oracle_cpu(rows, cols, I, J, V, tb)
         gf = 2.0 * flop / secs / 1e9
@@ -213,9 +233,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-coo-e2e", action="store_true", help="skip the second end-to-end figure (C pulled to host as sorted COO)")
     ap.add_argument("--keep-empty", type=int, default=0)
     ap.add_argument("--subpanels", type=int, default=0,
                     help="sequential tile-row panels per rank (0 = auto: config 5's C does not fit one GPU in tiled form "
@@ -259,13 +280,16 @@ def main():
         if world > 1:
             dist.barrier()
 
+    tile_products = 0
+
     def one_step(times=None, kern=None):
-        nnz = tiles = pairs = 0
+        nonlocal tile_products
+        nnz = tiles = pairs = tile_products = 0
         for pn in panels:               # this rank's panels, one after the other (results freed in between)
             tp = pem.Times()
             C = ctx.spgemm(A, B, times=tp, panel=pn)
             info = C.info
-            nnz += info.nnz; tiles += info.tiles; pairs += info.pairs
+            nnz += info.nnz; tiles += info.tiles; pairs += info.pairs; tile_products += info.tile_products
             C.free()
             if times is not None:
                 for f in ("step1_ms", "step2_ms", "step3_ms"):
@@ -284,7 +308,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count
-    step_ms, s1, s2, s3, kms = [], [], [], [], []
+    step_ms, own_ms, s1, s2, s3, kms = [], [], [], [], [], []
     for _ in range(args.steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -294,10 +318,12 @@ def main():
         sizes = one_step(t, kd)
         e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        own = e0.elapsed_time(e1)
+        ms = torch.tensor([own], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         step_ms.append(float(ms.item()))
+        own_ms.append(own)
         s1.append(t.step1_ms); s2.append(t.step2_ms); s3.append(t.step3_ms)
         kms.append(kd)
     launches = ctx.launch_count - launches0
@@ -305,55 +331,103 @@ def main():
     c_nnz, c_tiles, c_pairs = (int(x) for x in sizes.tolist())
     ms_per_step = float(np.mean(step_ms))
     value = 2.0 * flop / (ms_per_step * 1e6)
+    # per-rank figures (imbalance is visible in rank_ms; the dominant kernel's time is the slowest rank's)
+    kern_own = {k: float(np.mean([d[k] for d in kms])) for k in kms[0]}
+    per_rank = torch.tensor([float(np.mean(own_ms)), float(np.mean(s1)), float(np.mean(s2)), float(np.mean(s3))] +
+                            [kern_own[k] for k in sorted(kern_own)] + [float(tile_products)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
+        per_rank_all = torch.stack(gathered).cpu().numpy()
+    else:
+        per_rank_all = per_rank.cpu().numpy()[None, :]
 
-    # ---- end to end through the C ABI with HOST buffers: H2D of the COO, conversion, SpGEMM,
-    #      D2H of the result summary (nnz/tiles + device-reduced checksum), every step
-    e2e_ms = []
+    # ---- end to end through the C ABI with HOST buffers: H2D of the COO, conversion, SpGEMM, and
+    #      (a) D2H of the result summary (sizes + device-reduced checksum) or (b) D2H of C itself as sorted COO
+    #      into pinned host buffers (pem_result_to_coo), every step
     e2e_warm = 2            # untimed: the first end-to-end passes grow the memory pool (cudaMalloc inside), like the W warm-up steps
-    for _ in range(e2e_warm + max(3, min(args.steps, 5))):
+    h2d_rank = 0
+
+    def e2e_pass(coo_bufs=None):
+        nonlocal h2d_rank
         barrier()
         t0 = time.perf_counter()
         if world > 1:       # each rank uploads 1/world of the COO, NVLink all-gather, conversion from device arrays
             dI, dJ, dV, h2d_rank = pdist.upload_coo_sharded(tI, tJ, tV, torch.device("cuda", local_rank))
             torch.cuda.current_stream().synchronize()
             A2 = ctx.convert_coo(rows, cols, dI.data_ptr(), dJ.data_ptr(), dV.data_ptr(), nnz=I.size)
-            B2 = ctx.transpose(A2) if tb else A2
         else:
             A2 = ctx.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
-            B2 = ctx.transpose(A2) if tb else A2        # A^T from A's tiles, on the device
-        chk = [0.0, 0.0]
+        B2 = ctx.transpose(A2) if tb else A2            # A^T from A's tiles, on the device
+        pulled = 0
         for pn in panels:
             C2 = ctx.spgemm(A2, B2, panel=pn)
-            s_, a_ = C2.checksum()
-            chk[0] += s_; chk[1] += a_
+            if coo_bufs is None:
+                C2.checksum()
+            else:
+                n = C2.info.nnz
+                assert n <= coo_bufs[0].numel(), "pinned COO buffers too small for this panel"
+                C2.to_coo_into(coo_bufs[0].data_ptr(), coo_bufs[1].data_ptr(), coo_bufs[2].data_ptr())
+                pulled += 16 * n
             C2.free()
         ctx.sync()
-        ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3, float(pulled)], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        e2e_ms.append(float(ms.item()))
+            ms_max = ms.clone(); dist.all_reduce(ms_max, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ms, op=dist.ReduceOp.SUM)
+            ms[0] = ms_max[0]
         if B2 is not A2:
             B2.free()
         A2.free()
+        return float(ms[0].item()), int(ms[1].item())
+
+    e2e_ms = [e2e_pass()[0] for _ in range(e2e_warm + max(3, min(args.steps, 5)))]
     e2e_t = float(np.mean(e2e_ms[e2e_warm:]))
     h2d = int(I.nbytes + J.nbytes + V.nbytes) if world == 1 else int(h2d_rank) * world
-    d2h = (2 * 1024 * 2 * 8 + 3 * 8 * 16) * sub     # checksum partials + the size read-backs of one step
+    d2h = (2 * 1024 * 2 * 8 + 3 * 8 * 16) * sub * world    # checksum partials + the size read-backs of one step, all ranks
+    e2e_coo = None
+    if not args.no_coo_e2e:
+        # largest panel of this rank decides the pinned buffer size (panels are flop-balanced: 1.25x the mean is a safe bound, checked)
+        cap = int(1.25 * c_nnz / (world * sub)) + (1 << 20)
+        bufs = (torch.empty(cap, dtype=torch.int32, pin_memory=True), torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                torch.empty(cap, dtype=torch.float64, pin_memory=True))
+        runs = [e2e_pass(bufs) for _ in range(1 + 3)]
+        coo_t = float(np.mean([r[0] for r in runs[1:]]))
+        e2e_coo = {"value": 2.0 * flop / (coo_t * 1e6), "unit": "GFLOP/s", "ms_per_step": coo_t,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": runs[-1][1], "steps": 3, "warmup": 1,
+                   "what": "as e2e, but C itself is pulled into pinned host buffers as (row, col)-sorted COO through "
+                           "pem_result_to_coo: 16 bytes per nonzero of C"}
+        del bufs
 
     if rank == 0:
         peak, peak_src = hbm_peak()
         ai = A.info; bi = B.info
         bytes_alg = algorithmic_bytes(ai.rows, ai.nnz, bi.rows, bi.nnz, ai.rows, c_nnz)
-        t3 = float(np.mean(s3))
-        step_t = {"step1": float(np.mean(s1)), "step2": float(np.mean(s2)), "step3": t3}
+        names = sorted(kern_own)
+        rank_ms = [float(x) for x in per_rank_all[:, 0]]
+        slow = int(np.argmax(per_rank_all[:, 0]))          # the rank that sets the step time
+        t3 = float(per_rank_all[slow, 3])
+        step_t = {"step1": float(per_rank_all[slow, 1]), "step2": float(per_rank_all[slow, 2]), "step3": t3}
         # the dominant KERNEL: four kernels are bracketed by CUDA events on the engine's own stream inside
-        # pem_spgemm (pem_ctx_kernel_ms); their averages over the timed steps are taken live, here
-        kern_t = {k: float(np.mean([d[k] for d in kms])) for k in kms[0]}
+        # pem_spgemm (pem_ctx_kernel_ms); their averages over the timed steps are taken live, here (slowest rank)
+        kern_t = {k: float(per_rank_all[slow, 4 + i]) for i, k in enumerate(names)}
         dom = max(kern_t, key=kern_t.get)
+        sort_passes = ctx.last_sort_passes
         dom_kernel = {"k_expand": "k_expand (step 1: tile-product expansion + occupancy filter)",
-                      "radix_sort": "cub::DeviceRadixSort onesweep passes (step 1: sort of the kept tile pairs)",
+                      "radix_sort": ("no sort (per-row bitmap path of step 1)" if sort_passes < 0 else
+                                     "k_row_sort (step 1: block-local bitonic sort of each C' row's tile pairs)" if sort_passes == 0 else
+                                     f"cub::DeviceRadixSort onesweep, {sort_passes} passes (step 1: sort of the kept tile pairs)"),
                       "k_step2_pairs": "k_step2_pairs (step 2: 16x16 boolean products, pair-parallel)",
                       "step3_numeric": "k_step3_entries (step 3: fp64 numeric accumulation)"}[dom]
         td = kern_t[dom]
+        # compulsory bytes of each timed kernel, whole job; the numeric kernel's are the
+        # algorithmic bytes of the product (it reads A and B and writes C)
+        P = int(per_rank_all[:, -1].sum())
+        kernel_bytes = {"k_expand": 2 * P + 12 * c_pairs,
+                        "radix_sort": 2 * 12 * c_pairs * max(1, sort_passes),
+                        "k_step2_pairs": (8 + 64 + 4) * c_pairs + 32 * c_tiles,
+                        "step3_numeric": bytes_alg}
+        kb = kernel_bytes[dom]
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(f"config{args.config}", {}).get(dom)
@@ -363,17 +437,19 @@ def main():
             "metric": "spgemm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": CONFIG_TEXT[args.config], "product": "A*A^T" if tb else "A^2",
-                       "flop": flop, "nnz_A": int(ai.nnz), "nnz_C": c_nnz, "C_tiles": c_tiles, "tile_pairs": c_pairs,
-                       "parallelism": f"tile-row panels x{world}, B replicated" + (f"; {sub} sequential sub-panels per GPU" if sub > 1 else ""),
-                       "l2": "no flush: each step streams > 1 GB (C + C' metadata), far above the 126 MB L2",
-                       "keep_empty_tiles": args.keep_empty},
+            "config": static_config(args.config, tb),
+            "workload_stats": {"flop": flop, "nnz_A": int(ai.nnz), "nnz_C": c_nnz, "C_tiles": c_tiles, "tile_pairs": c_pairs,
+                               "parallelism": f"tile-row panels x{world}, B replicated" + (f"; {sub} sequential sub-panels per GPU" if sub > 1 else ""),
+                               "l2": "no flush: each step streams > 1 GB (C + C' metadata), far above the 126 MB L2",
+                               "keep_empty_tiles": args.keep_empty},
+            "rank_ms": rank_ms,
             "step_ms": step_t, "kernel_ms": kern_t,
-            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": bytes_alg / (td * 1e6) if td > 0 else None,
-                         "peak": peak, "unit": "GB/s", "frac": (bytes_alg / (td * 1e6) / peak) if td > 0 else None,
-                         "traffic": traffic, "algorithmic_bytes": bytes_alg, "peak_source": peak_src,
-                         "numeric_kernel_frac": (bytes_alg / (t3 * 1e6) / peak) if t3 > 0 else None,
-                         "whole_spgemm_frac": bytes_alg / (ms_per_step * 1e6) / peak},
+            # at N GPUs the job's bytes are split over N kernels running side by side: the peak is N x one GPU's
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": kb / (td * 1e6) if td > 0 else None,
+                         "peak": peak * world, "unit": "GB/s", "frac": (kb / (td * 1e6) / (peak * world)) if td > 0 else None,
+                         "traffic": traffic, "algorithmic_bytes": bytes_alg, "kernel_bytes": kb, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
+                         "numeric_kernel_frac": (bytes_alg / (kern_t["step3_numeric"] * 1e6) / (peak * world)) if kern_t.get("step3_numeric", 0) > 0 else None,
+                         "whole_spgemm_frac": bytes_alg / (ms_per_step * 1e6) / (peak * world)},
             "e2e": {"value": 2.0 * flop / (e2e_t * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_t,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": len(e2e_ms) - e2e_warm, "warmup": e2e_warm,
@@ -382,6 +458,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if e2e_coo is not None:
+            line["e2e_coo"] = e2e_coo
         if world == 1 and not args.no_cpu_baseline:
             f2, secs, thr = oracle_cpu(rows, cols, I, J, V, tb)
             assert f2 == flop, "engine and oracle disagree on flop"

@@ -115,6 +115,9 @@ int64_t pem_ctx_launch_count(const pem_ctx* ctx);
  * the last pem_spgemm / pem_spgemm_panel call: [0] k_expand (step 1 product expansion), [1] the
  * step-1 radix sort, [2] k_step2_pairs, [3] the step-3 numeric kernel.  Returns the count (4). */
 int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n);
+/* How step 1 of the last product ordered its tile pairs: -1 = no sort (per-row bitmap path), 0 = block-local
+ * sort of every C' row in shared memory, n > 0 = n passes of the global radix sort (labels the KT slot [1]). */
+int pem_ctx_last_sort_passes(const pem_ctx* ctx);
 /* Allocations that missed the context's block cache and went to the CUDA pool since creation
  * (diagnostic: a steady-state loop should not add any). */
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx);

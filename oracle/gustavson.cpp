@@ -27,6 +27,8 @@
 extern "C" {
 
 int oracle_max_threads() { return omp_get_max_threads(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1: a caller that wants all host cores says so
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 // COO (any order, no duplicates) -> CSR with columns ascending inside each row.
 // Returns 0, or -1 if a coordinate is out of range, -2 if a duplicate (i,j) exists.

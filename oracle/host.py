@@ -35,6 +35,8 @@ def lib():
         build()
         L = C.CDLL(_LIB_PATH)
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_threads.restype = None
+        L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_coo_to_csr.restype = C.c_int
         L.oracle_coo_to_csr.argtypes = [C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i64p, _i32p, _f64p]
         L.oracle_csr_transpose.restype = None
@@ -48,6 +50,12 @@ def lib():
                                             _i64p, _i32p, _f64p]
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """Use n OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1); returns the count in effect."""
+    lib().oracle_set_threads(int(n))
+    return int(lib().oracle_max_threads())
 
 
 @dataclass

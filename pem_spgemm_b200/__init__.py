@@ -71,7 +71,7 @@ class ResultInfo(C.Structure):
 
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
-    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
+    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
     "pem_tiled_info_get",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
@@ -107,6 +107,7 @@ def load():
         "pem_ctx_stream": (vp, [vp]),
         "pem_ctx_sync": (C.c_int, [vp]),
         "pem_ctx_launch_count": (i64, [vp]),
+        "pem_ctx_last_sort_passes": (C.c_int, [vp]),
         "pem_ctx_pool_bytes": (i64, [vp]),
         "pem_ctx_pool_mallocs": (i64, [vp]),
         "pem_ctx_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
@@ -192,6 +193,10 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(load().pem_ctx_launch_count(self._h))
+
+    @property
+    def last_sort_passes(self) -> int:
+        return int(load().pem_ctx_last_sort_passes(self._h))
 
     def kernel_ms(self) -> dict:
         """Device time of the individually timed kernels of the last spgemm call (CUDA events)."""
@@ -316,6 +321,12 @@ class Result:
         v = np.empty(n, np.float64) if values else None
         self.ctx._check(load().pem_result_to_coo(self.ctx._h, self._h, _ptr(r), _ptr(c), _ptr(v)))
         return r, c, v
+
+    def to_coo_into(self, rows_ptr, cols_ptr, vals_ptr):
+        """Same, into caller-owned HOST buffers given as integer addresses (pinned memory for full PCIe
+        speed); each must hold ``info.nnz`` entries; 0 skips an array."""
+        self.ctx._check(load().pem_result_to_coo(self.ctx._h, self._h, C.c_void_p(rows_ptr or None),
+                                                 C.c_void_p(cols_ptr or None), C.c_void_p(vals_ptr or None)))
 
     def checksum(self):
         s, a = C.c_double(), C.c_double()

@@ -419,6 +419,7 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
                     const int32_t* I, const int32_t* J, const double* V, int transpose,
                     pem_tiled** out, pem_times* times)
 {
+    PEM_RANGE("pem_convert_coo");
     if (!ctx || !out) return PEM_ERR_ARG;
     *out = nullptr;
     if (rows < 0 || cols < 0 || nnz < 0) return ctx->fail(PEM_ERR_ARG, "negative size");
@@ -630,6 +631,7 @@ extern "C" {
 
 int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
 {
+    PEM_RANGE("pem_tiled_transpose");
     if (!ctx || !A || !out) return PEM_ERR_ARG;
     *out = nullptr;
     PEM_CK(cudaSetDevice(ctx->device));

@@ -176,6 +176,7 @@ int pem_ctx_sync(pem_ctx* ctx)
 }
 
 int64_t pem_ctx_launch_count(const pem_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int pem_ctx_last_sort_passes(const pem_ctx* ctx) { return ctx ? ctx->last_sort_passes : -1; }
 
 int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n)
 {

@@ -1,6 +1,7 @@
 // Internal definitions shared by the engine's translation units (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -29,6 +30,7 @@ struct pem_ctx {
     cudaMemPool_t pool = nullptr;
     std::string err;
     int64_t launches = 0;        // kernels of this library launched on the stream
+    int last_sort_passes = -1;   // step 1 of the last product: -1 = no sort (bitmap path), 0 = block-local row sort, n = n radix passes
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
     int opt_owner = 0;           // PEM_OPT_OWNER: 0 / 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel
@@ -61,6 +63,13 @@ struct pem_ctx {
         return PEM_ERR_CUDA;
     }
 };
+
+// NVTX range around a stage (shows up in Nsight Systems / ncu --nvtx; a no-op without a tool attached)
+struct PemRange {
+    explicit PemRange(const char* name) { nvtxRangePushA(name); }
+    ~PemRange() { nvtxRangePop(); }
+};
+#define PEM_RANGE(name) PemRange pem_range__(name)
 
 #define PEM_CK(call)                                                                     \
     do {                                                                                 \

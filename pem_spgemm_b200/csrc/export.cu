@@ -116,14 +116,16 @@ int pem_result_to_coo_device(pem_ctx* ctx, const pem_result* C, int32_t* d_rows,
 
 int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, double* vals)
 {
+    PEM_RANGE("pem_result_to_coo");
     if (!ctx || !C) return PEM_ERR_ARG;
     int32_t *dr = nullptr, *dc = nullptr;
     double* dv = nullptr;
     size_t n = (size_t)C->nnz;
-    if (rows) PEM_TRY(pem_alloc(ctx, &dr, n));
-    if (cols) PEM_TRY(pem_alloc(ctx, &dc, n));
-    if (vals) PEM_TRY(pem_alloc(ctx, &dv, n));
-    int rc = pem_result_to_coo_device(ctx, C, dr, dc, dv, nullptr);
+    int rc = PEM_OK;
+    if (rows) rc = pem_alloc(ctx, &dr, n);
+    if (cols && rc == PEM_OK) rc = pem_alloc(ctx, &dc, n);
+    if (vals && rc == PEM_OK) rc = pem_alloc(ctx, &dv, n);
+    if (rc == PEM_OK) rc = pem_result_to_coo_device(ctx, C, dr, dc, dv, nullptr);
     if (rc == PEM_OK && n) {
         cudaError_t e = cudaSuccess;
         if (rows && e == cudaSuccess) e = cudaMemcpyAsync(rows, dr, n * 4, cudaMemcpyDeviceToHost, ctx->stream);

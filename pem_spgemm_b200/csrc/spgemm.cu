@@ -285,6 +285,7 @@ extern "C" {
 
 int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
 {
+    PEM_RANGE("pem_step2_symbolic");
     if (!ctx || !A || !B || !C) return PEM_ERR_ARG;
     if (C->stage != 1) return ctx->fail(PEM_ERR_ARG, "step 2 needs a result fresh from step 1");
     if (C->tiles >= 0x7fffffffLL)
@@ -361,6 +362,7 @@ int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C)
 int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
                      int32_t rb, int32_t re, pem_result** out, pem_times* times)
 {
+    PEM_RANGE("pem_spgemm_panel");
     if (!out) return PEM_ERR_ARG;
     *out = nullptr;
     PEM_TRY(check_operands(ctx, A, B, rb, re));

@@ -501,6 +501,7 @@ __global__ void k_set_i64(int64_t* p, int64_t idx, int64_t v) { p[idx] = v; }
 extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
                                   int32_t rb, int32_t re, pem_result** out)
 {
+    PEM_RANGE("pem_step1_symbolic");
     if (!out) return PEM_ERR_ARG;
     *out = nullptr;
     if (!ctx || !A || !B) return PEM_ERR_ARG;
@@ -510,6 +511,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     pem_result* C = new pem_result();
     C->rb = rb; C->re = re; C->rows = A->rows; C->cols = B->cols; C->tile_cols = B->tile_cols;
     const int nrows = re - rb;
+    ctx->last_sort_passes = -1;
     // small operands are launch-bound: the per-row bitmap path below needs ~8 launches and 2 host
     // syncs, expand-sort-compress ~20 and 3
     const bool small = (int64_t)A->tiles + B->tiles <= 65536 && B->tile_cols <= 65536;

@@ -531,6 +531,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         //  4.5 ms against 2.7 ms for the radix sort)
         if (longest <= RS_SMALL) by_rows = 1;
     }
+    ctx->last_sort_passes = by_rows ? 0 : (wbits + rbits + 7) / 8;
     if (by_rows) {
         KT_BEGIN(KT_SORT);
         k_row_sort<KeyT, 128, RS_SMALL_BITS><<<nrows, 128, RS_SMALL * 4, ctx->stream>>>(wbits, seg_off, key_a, val_a, key_b, val_b);

@@ -394,6 +394,7 @@ k_step3_numeric(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int
 
 extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
 {
+    PEM_RANGE("pem_step3_numeric");
     if (!ctx || !A || !B || !C) return PEM_ERR_ARG;
     if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
     PEM_CK(cudaSetDevice(ctx->device));

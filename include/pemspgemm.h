@@ -68,7 +68,13 @@ typedef enum pem_option {
     /* tuning of the tile-class kernel: a C' tile with at most SMALL_NNZ nonzeros (default 8) and at most
      * SMALL_PAIRS pairs (default 64) is handled by one thread, any other tile by one warp */
     PEM_OPT_S3_SMALL_NNZ = 4,
-    PEM_OPT_S3_SMALL_PAIRS = 5
+    PEM_OPT_S3_SMALL_PAIRS = 5,
+    /* 0 (default): when pem_convert_coo returns, the caller's I/J/V arrays are free again.
+     * 1: for HOST input, pem_convert_coo returns while the upload of V (half of the COO bytes) is still in
+     *    flight on the context's copy stream; V must stay valid and unmodified until pem_tiled_values_ready
+     *    (or any product / accessor that reads the values) has returned.  The symbolic steps 1 and 2 of a
+     *    product read masks only, so they overlap the upload: on config 4 end to end 51 -> 45 ms. */
+    PEM_OPT_ASYNC_VALUES = 6
 } pem_option;
 
 /* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are
@@ -137,6 +143,9 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
  * `[1]` mode without parsing, uploading and sorting the COO a second time (the reference converts
  * the file twice, spgemm.cu:778-792, 849-978).  Bit-identical to pem_convert_coo(..., transpose=1). */
 int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out);
+/* Blocks the host until the values of a tiled matrix converted under PEM_OPT_ASYNC_VALUES have left the
+ * caller's V array (immediate otherwise). */
+int pem_tiled_values_ready(pem_ctx* ctx, const pem_tiled* t);
 int pem_tiled_info_get(const pem_tiled* t, pem_tiled_info* info);
 void pem_tiled_free(pem_ctx* ctx, pem_tiled* t);
 

@@ -28,6 +28,7 @@ OPT_STEP1_PATH = 2
 OPT_OWNER = 3
 OPT_S3_SMALL_NNZ = 4
 OPT_S3_SMALL_PAIRS = 5
+OPT_ASYNC_VALUES = 6
 
 # pem_tiled_array / pem_result_array -> (index, dtype)
 T_ARRAYS = {
@@ -72,7 +73,7 @@ class ResultInfo(C.Structure):
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
     "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
-    "pem_tiled_info_get",
+    "pem_tiled_info_get", "pem_tiled_values_ready",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
     "pem_result_info_get", "pem_result_free", "pem_result_get", "pem_result_device_ptr",
@@ -114,6 +115,7 @@ def load():
         "pem_convert_coo": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
         "pem_tiled_transpose": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pem_tiled_info_get": (C.c_int, [vp, C.POINTER(TiledInfo)]),
+        "pem_tiled_values_ready": (C.c_int, [vp, vp]),
         "pem_tiled_free": (None, [vp, vp]),
         "pem_tiled_get": (C.c_int, [vp, vp, C.c_int, vp, C.c_size_t]),
         "pem_tiled_device_ptr": (vp, [vp, C.c_int]),
@@ -287,6 +289,10 @@ class Tiled:
         out = np.empty(n, dt)
         self.ctx._check(load().pem_tiled_get(self.ctx._h, self._h, idx, _ptr(out), out.nbytes))
         return out
+
+    def values_ready(self):
+        """Block until the engine no longer reads the host value array this matrix was converted from."""
+        self.ctx._check(load().pem_tiled_values_ready(self.ctx._h, self._h))
 
     def free(self):
         if self._h:

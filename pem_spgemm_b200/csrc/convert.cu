@@ -57,14 +57,16 @@ k_make_keys(const int32_t* __restrict__ I, const int32_t* __restrict__ J, int64_
 // sorted original position (the sort carries 4-byte positions, not 8-byte values, and the values'
 // host->device copy overlaps it)
 __global__ void __launch_bounds__(256)
-k_rc_idx_vals(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, const double* __restrict__ V,
-              int64_t nnz, uint8_t* __restrict__ rc, double* __restrict__ vals)
+k_rc_idx(const uint64_t* __restrict__ keys, int64_t nnz, uint8_t* __restrict__ rc)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < nnz) {
-        rc[e] = (uint8_t)(keys[e] & 255u);
-        vals[e] = V[pos[e]];
-    }
+    if (e < nnz) rc[e] = (uint8_t)(keys[e] & 255u);
+}
+__global__ void __launch_bounds__(256)
+k_gather_vals(const uint32_t* __restrict__ pos, const double* __restrict__ V, int64_t nnz, double* __restrict__ vals)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) vals[e] = V[pos[e]];
 }
 
 // predicate for the tile census: position e starts a new tile
@@ -492,18 +494,39 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         CV_TRY(pem_alloc(ctx, &tmp, std::max(tmp_bytes, tmp2)));
         CV_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, pos, pos_sorted, nnz, 0, 8 + cb + rb, ctx->stream));
         CV_CK(cub::DeviceSelect::If(tmp, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
-        if (own) CV_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[1], 0));     // the values have arrived
         CV_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)nnz));
-        k_rc_idx_vals<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(keys_sorted, pos_sorted, dV, nnz, T->rc_idx, T->vals);
+        k_rc_idx<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(keys_sorted, nnz, T->rc_idx);
         ++ctx->launches;
         CV_CK(cudaGetLastError());
+        if (own) {
+            // The values are gathered into tile order on the COPY stream, behind their upload; the engine's
+            // stream does not wait here: tile build and the symbolic steps of a product need masks only, so
+            // they run underneath the upload.  pem_tiled_wait_vals joins the two streams for the first reader.
+            CV_CK(cudaEventCreateWithFlags(&T->ev_vals, cudaEventDisableTiming));
+            CV_CK(cudaEventRecord(ctx->ev_copy[0], ctx->stream));                  // sorted positions are final
+            CV_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
+            k_gather_vals<<<pem_div_up(nnz, 256), 256, 0, ctx->copy_stream>>>(pos_sorted, dV, nnz, T->vals);
+            ++ctx->launches;
+            CV_CK(cudaGetLastError());
+            CV_CK(cudaEventRecord(T->ev_vals, ctx->copy_stream));
+            T->vals_pending = true;
+            T->pend_buf[0] = pos_sorted; T->pend_buf[1] = dV;                      // freed once the gather is known to be done
+            pos_sorted = nullptr; dV = nullptr;
+        } else {
+            k_gather_vals<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(pos_sorted, dV, nnz, T->vals);
+            ++ctx->launches;
+            CV_CK(cudaGetLastError());
+        }
         pem_free(ctx, pos);
         pem_free(ctx, pos_sorted);
         CV_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CV_CK(cudaStreamSynchronize(ctx->stream));
         pem_free(ctx, tmp);
         pem_free(ctx, keys);
-        if (own) { pem_free(ctx, dI); pem_free(ctx, dJ); pem_free(ctx, dV); }
+        if (own) { pem_free(ctx, dI); pem_free(ctx, dJ); }
+        // default contract: the caller's arrays are free again when this call returns, so the host waits for the
+        // values' upload (not for their gather); PEM_OPT_ASYNC_VALUES hands that wait to the caller
+        if (own && !ctx->opt_async_vals) CV_CK(cudaEventSynchronize(ctx->ev_copy[1]));
         if (ctx->h_scalars[SC_ERR] & 1) {
             pem_free(ctx, keys_sorted); pem_free(ctx, start_tmp);
             return fail(ctx->fail(PEM_ERR_RANGE, "COO coordinate outside the matrix"));
@@ -562,6 +585,19 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
 
 }  // extern "C"
 
+// Join the engine's stream with the upload + gather of a freshly converted operand's values (see
+// pem_convert_coo); a no-op for every later call.
+int pem_tiled_wait_vals(pem_ctx* ctx, const pem_tiled* Tc)
+{
+    pem_tiled* T = const_cast<pem_tiled*>(Tc);
+    if (!T->vals_pending) return PEM_OK;
+    PEM_CK(cudaStreamWaitEvent(ctx->stream, T->ev_vals, 0));
+    // the staging buffers go back to the cache in the engine's stream order, i.e. behind the wait above
+    for (void*& b : T->pend_buf) { if (b) pem_free_bytes(ctx, b); b = nullptr; }
+    T->vals_pending = false;
+    return PEM_OK;
+}
+
 // Row slices of a tiled matrix, built once and cached on the handle (the handle is logically
 // const for the caller; the cache is the one mutable part).
 int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* Bc)
@@ -612,6 +648,7 @@ int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* Tc, bool as_a, bool as_
         T->row_rec = rec;
     }
     if (as_b && !T->col_rec) {
+        PEM_TRY(pem_tiled_wait_vals(ctx, T));
         uint32_t* rec = nullptr;
         double* vt = nullptr;
         PEM_TRY(pem_alloc(ctx, &rec, n16));
@@ -635,6 +672,7 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
     if (!ctx || !A || !out) return PEM_ERR_ARG;
     *out = nullptr;
     PEM_CK(cudaSetDevice(ctx->device));
+    PEM_TRY(pem_tiled_wait_vals(ctx, A));
     pem_tiled* T = new pem_tiled();
     T->rows = A->cols; T->cols = A->rows; T->nnz = A->nnz;
     T->tile_rows = A->tile_cols; T->tile_cols = A->tile_rows; T->tiles = A->tiles;

@@ -154,6 +154,7 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
             if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0..3");
             ctx->opt_owner = (int)value;
             return PEM_OK;
+        case PEM_OPT_ASYNC_VALUES: ctx->opt_async_vals = value != 0; return PEM_OK;
         case PEM_OPT_S3_SMALL_NNZ:
             if (value < 0 || value > 256) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_S3_SMALL_NNZ must be 0..256");
             ctx->opt_s3_small_e = (int)value;
@@ -224,9 +225,17 @@ static const void* tiled_array(const pem_tiled* t, int which, size_t* bytes)
     return nullptr;
 }
 
+int pem_tiled_values_ready(pem_ctx* ctx, const pem_tiled* t)
+{
+    if (!ctx || !t) return PEM_ERR_ARG;
+    if (t->vals_pending) PEM_CK(cudaEventSynchronize(t->ev_vals));
+    return PEM_OK;
+}
+
 const void* pem_tiled_device_ptr(const pem_tiled* t, int which)
 {
     size_t b;
+    if (t && which == PEM_T_VALS && t->vals_pending) cudaEventSynchronize(t->ev_vals);   // no context here: wait on the host
     return t ? tiled_array(t, which, &b) : nullptr;
 }
 
@@ -238,6 +247,7 @@ int pem_tiled_get(pem_ctx* ctx, const pem_tiled* t, int which, void* host_dst, s
     if (!src && have == 0 && which > PEM_T_ROW_COL_IDX) return ctx->fail(PEM_ERR_ARG, "unknown tiled array");
     if (bytes != have) return ctx->fail(PEM_ERR_ARG, "pem_tiled_get: size mismatch");
     if (bytes == 0) return PEM_OK;
+    if (which == PEM_T_VALS) PEM_TRY(pem_tiled_wait_vals(ctx, t));
     PEM_CK(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     return PEM_OK;
@@ -246,6 +256,8 @@ int pem_tiled_get(pem_ctx* ctx, const pem_tiled* t, int which, void* host_dst, s
 void pem_tiled_free(pem_ctx* ctx, pem_tiled* t)
 {
     if (!ctx || !t) return;
+    (void)pem_tiled_wait_vals(ctx, t);       // a gather still in flight on the copy stream writes t->vals
+    if (t->ev_vals) cudaEventDestroy(t->ev_vals);
     pem_free(ctx, t->vals); pem_free(ctx, t->tile_nnz_ptr); pem_free(ctx, t->masks);
     pem_free(ctx, t->masks_t); pem_free(ctx, t->row_ptr); pem_free(ctx, t->tile_row_ptr);
     pem_free(ctx, t->tile_col_idx); pem_free(ctx, t->tile_row_idx); pem_free(ctx, t->col_occ);

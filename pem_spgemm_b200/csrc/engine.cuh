@@ -34,6 +34,7 @@ struct pem_ctx {
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
     int opt_owner = 0;           // PEM_OPT_OWNER: 0 / 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel
+    int opt_async_vals = 0;      // PEM_OPT_ASYNC_VALUES: pem_convert_coo returns while the values' upload is still in flight
     int opt_s3_small_e = 8;      // PEM_OPT_S3_SMALL_NNZ: step 3 handles a tile with at most this many nonzeros ...
     int opt_s3_small_np = 64;    // PEM_OPT_S3_SMALL_PAIRS: ... and at most this many pairs with one thread
     int sm_count = 148;
@@ -131,6 +132,12 @@ struct pem_tiled {
     uint16_t* col_occ = nullptr;      // [tiles]
     uint16_t* row_occ = nullptr;      // [tiles]
     uint8_t* rc_idx = nullptr;        // [nnz] (r<<4)|c of every value, tile-major (the reference's *tiles_rowColIdx)
+    // conversion from host memory: the values' upload and their gather into tile order run on the context's
+    // copy stream, BEHIND the call that returns this handle, so the symbolic steps of a product (which read
+    // masks only) overlap them; whoever reads `vals` first makes the engine's stream wait (pem_tiled_wait_vals)
+    cudaEvent_t ev_vals = nullptr;    // recorded on the copy stream after the gather
+    bool vals_pending = false;
+    void* pend_buf[2] = {nullptr, nullptr};   // staging buffers the gather still reads (sorted positions, uploaded values)
     std::vector<int32_t> h_tile_row_ptr;  // host copy of tile_row_ptr: panel calls find their tile range without a device read
     // row slices, built on first use as a B operand of step 1 (pem_tiled_build_srow): for every
     // matrix row s the ids of the tiles that hold a nonzero of row s (in no particular order)
@@ -188,4 +195,5 @@ int pem_scan_exclusive_i64(pem_ctx* ctx, int64_t* d_inout, int64_t n);  // in pl
 extern "C" int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C);
 int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C);  // step1_esc.cu
 int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* B);                              // convert.cu
+int pem_tiled_wait_vals(pem_ctx* ctx, const pem_tiled* T);                               // convert.cu
 int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* T, bool as_a, bool as_b);       // convert.cu

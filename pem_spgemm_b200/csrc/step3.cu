@@ -398,6 +398,8 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
     if (!ctx || !A || !B || !C) return PEM_ERR_ARG;
     if (C->stage != 2) return ctx->fail(PEM_ERR_ARG, "step 3 needs a result fresh from step 2");
     PEM_CK(cudaSetDevice(ctx->device));
+    PEM_TRY(pem_tiled_wait_vals(ctx, A));        // freshly converted operands: the values may still be on their way
+    PEM_TRY(pem_tiled_wait_vals(ctx, B));
     PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
     const bool by_records = C->pair_hit != nullptr;         // step 2 ran the pair kernel
     // the class kernel reads every nonzero's (r, c) from Ctiles_rowColIdx; the entry-owner kernel derives it

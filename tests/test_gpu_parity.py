@@ -221,6 +221,34 @@ def test_panels_concatenate_to_full_result(engine, k, nparts):
     A.free(); B.free()
 
 
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_async_values_conversion(engine, k):
+    """PEM_OPT_ASYNC_VALUES: pem_convert_coo returns while the values are still uploading from pinned host
+    memory; the product (whose steps 1-2 overlap the upload), the accessors, the transpose and an early free
+    must all see finished values."""
+    import torch
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    tI = torch.from_numpy(I.copy()).pin_memory(); tJ = torch.from_numpy(J.copy()).pin_memory(); tV = torch.from_numpy(V.copy()).pin_memory()
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    engine.set_option(pem.OPT_ASYNC_VALUES, 1)
+    try:
+        for rep in range(3):
+            A = engine.convert_coo(rows, cols, tI.numpy(), tJ.numpy(), tV.numpy())
+            if rep == 0:
+                B = engine.transpose(A) if tb else A
+                C = engine.spgemm(A, B)
+                _assert_same_C(C, oC)
+                C.free()
+                if B is not A:
+                    B.free()
+            elif rep == 1:
+                assert np.array_equal(A.array("vals"), tiles.tile_format(rows, cols, I, J, V).vals)
+                A.values_ready()
+            A.free()                       # rep 2: freed with the upload possibly still in flight
+    finally:
+        engine.set_option(pem.OPT_ASYNC_VALUES, 0)
+
+
 def test_device_pointer_input_and_pool_reuse(engine):
     import torch
     rows, cols, I, J, V = synth.random_sparse(2000, 2000, 30000, seed=8)

@@ -74,7 +74,20 @@ typedef enum pem_option {
      *    flight on the context's copy stream; V must stay valid and unmodified until pem_tiled_values_ready
      *    (or any product / accessor that reads the values) has returned.  The symbolic steps 1 and 2 of a
      *    product read masks only, so they overlap the upload: on config 4 end to end 51 -> 45 ms. */
-    PEM_OPT_ASYNC_VALUES = 6
+    PEM_OPT_ASYNC_VALUES = 6,
+    /* step-2 mask kernel: 0 (default) / 1 = one lane per (A tile, B tile) pair walking the shorter nonzero
+     * list; 2 = sixteen lanes per C' tile, row masks exchanged by shuffles (bit-identical; measured slower) */
+    PEM_OPT_STEP2_KERNEL = 7,
+    /* diagnostics: 1 = host-side timeline of step 1 on stderr (where the host waits), 2 = also per-phase cycle
+     * counters of the bitmap kernels */
+    PEM_OPT_TRACE = 8,
+    /* expand-sort-compress variants that are otherwise chosen by size (tests force them): bit 0 = count per chunk,
+     * scan, write exactly (instead of staging at product bases and compacting), bit 1 = never use the block-local
+     * row sort */
+    PEM_OPT_ESC_VARIANT = 9,
+    /* the context keeps freed device blocks for reuse; once more than this many MiB are cached they are handed
+     * back to the driver (default: 80 % of the memory free at pem_ctx_create); see pem_ctx_trim */
+    PEM_OPT_CACHE_LIMIT_MB = 10
 } pem_option;
 
 /* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are
@@ -129,6 +142,9 @@ int pem_ctx_last_sort_passes(const pem_ctx* ctx);
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx);
 /* Bytes currently reserved by the context's pool (diagnostic). */
 int64_t pem_ctx_pool_bytes(const pem_ctx* ctx);
+/* Hands every cached (freed, not yet reused) device block back to the driver: call between workloads when
+ * another allocator in the process (torch, NCCL) needs the memory.  Synchronises the context's stream. */
+int pem_ctx_trim(pem_ctx* ctx);
 
 /* ---- conversion: COO -> tiled CSR ----------------------------------------------------- */
 /* Replaces spgemm.cu:821-1066 (decide_which_tile, the thrust sort/unique/reduce pipeline,
@@ -138,6 +154,11 @@ int64_t pem_ctx_pool_bytes(const pem_ctx* ctx);
 int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
                     const int32_t* I, const int32_t* J, const double* V, int transpose,
                     pem_tiled** out, pem_times* times);
+/* Same from CSR (the reference builds a CSR on its way to tiles, spgemm.cu:894-928; SURVEY.md section 8f rank 4
+ * asks for a CSR-in entry): row_ptr[rows+1] (int32, starts at 0), col_idx / vals [row_ptr[rows]], all three host or
+ * all three device pointers; columns need not be sorted inside a row; duplicates are rejected. */
+int pem_convert_csr(pem_ctx* ctx, int32_t rows, int32_t cols, const int32_t* row_ptr, const int32_t* col_idx,
+                    const double* vals, int transpose, pem_tiled** out, pem_times* times);
 /* The transpose of a tiled matrix, built on the device from A's tiles (tile keys re-sorted, masks and
  * column masks swap roles, values moved to their column-major slots): B = A^T for the CLI's
  * `[1]` mode without parsing, uploading and sorting the COO a second time (the reference converts
@@ -215,6 +236,9 @@ const void* pem_result_device_ptr(const pem_result* C, int which);
 /* Tiled C -> COO sorted by (row, col): sanitize_C + stable_sort + D2H (spgemm.cu:1493-1543).
  * rows/cols/vals are HOST buffers of pem_result_info.nnz entries (any may be NULL to skip). */
 int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, double* vals);
+/* Tiled C -> CSR with ascending columns: row_ptr is a HOST buffer of (rows covered by the result) + 1 int64 entries
+ * (the whole C: rows + 1), cols / vals HOST buffers of nnz entries (any may be NULL to skip). */
+int pem_result_to_csr(pem_ctx* ctx, const pem_result* C, int64_t* row_ptr, int32_t* cols, double* vals);
 /* Same, but into DEVICE buffers, plus CSR row pointer (int64[rows_in_panel*16+1], may be NULL). */
 int pem_result_to_coo_device(pem_ctx* ctx, const pem_result* C, int32_t* d_rows, int32_t* d_cols,
                              double* d_vals, int64_t* d_row_ptr);

@@ -29,6 +29,10 @@ OPT_OWNER = 3
 OPT_S3_SMALL_NNZ = 4
 OPT_S3_SMALL_PAIRS = 5
 OPT_ASYNC_VALUES = 6
+OPT_STEP2_KERNEL = 7
+OPT_TRACE = 8
+OPT_ESC_VARIANT = 9
+OPT_CACHE_LIMIT_MB = 10
 
 # pem_tiled_array / pem_result_array -> (index, dtype)
 T_ARRAYS = {
@@ -72,12 +76,12 @@ class ResultInfo(C.Structure):
 
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
-    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_convert_coo", "pem_tiled_transpose",
+    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_ctx_trim", "pem_convert_coo", "pem_convert_csr", "pem_tiled_transpose",
     "pem_tiled_info_get", "pem_tiled_values_ready",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
     "pem_result_info_get", "pem_result_free", "pem_result_get", "pem_result_device_ptr",
-    "pem_result_to_coo", "pem_result_to_coo_device", "pem_result_checksum", "pem_mtx_read", "pem_mtx_write",
+    "pem_result_to_coo", "pem_result_to_csr", "pem_result_to_coo_device", "pem_result_checksum", "pem_mtx_read", "pem_mtx_write",
     "pem_free_host",
 ]
 
@@ -110,9 +114,11 @@ def load():
         "pem_ctx_launch_count": (i64, [vp]),
         "pem_ctx_last_sort_passes": (C.c_int, [vp]),
         "pem_ctx_pool_bytes": (i64, [vp]),
+        "pem_ctx_trim": (C.c_int, [vp]),
         "pem_ctx_pool_mallocs": (i64, [vp]),
         "pem_ctx_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
         "pem_convert_coo": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
+        "pem_convert_csr": (C.c_int, [vp, i32, i32, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
         "pem_tiled_transpose": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pem_tiled_info_get": (C.c_int, [vp, C.POINTER(TiledInfo)]),
         "pem_tiled_values_ready": (C.c_int, [vp, vp]),
@@ -131,6 +137,7 @@ def load():
         "pem_result_get": (C.c_int, [vp, vp, C.c_int, vp, C.c_size_t]),
         "pem_result_device_ptr": (vp, [vp, C.c_int]),
         "pem_result_to_coo": (C.c_int, [vp, vp, vp, vp, vp]),
+        "pem_result_to_csr": (C.c_int, [vp, vp, vp, vp, vp]),
         "pem_result_to_coo_device": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "pem_result_checksum": (C.c_int, [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "pem_mtx_read": (C.c_int, [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(vp),
@@ -210,6 +217,10 @@ class Context:
     def pool_mallocs(self) -> int:
         return int(load().pem_ctx_pool_mallocs(self._h))
 
+    def trim(self):
+        """Hand the cached device blocks back to the driver."""
+        self._check(load().pem_ctx_trim(self._h))
+
     @property
     def pool_bytes(self) -> int:
         return int(load().pem_ctx_pool_bytes(self._h))
@@ -227,6 +238,17 @@ class Context:
         rc = load().pem_convert_coo(self._h, rows, cols, nnz, _ptr(I), _ptr(J), _ptr(V), int(bool(transpose)),
                                     C.byref(h), C.byref(times) if times is not None else None)
         self._keep = None
+        self._check(rc)
+        return Tiled(self, h)
+
+    def convert_csr(self, rows, cols, row_ptr, col_idx, vals, transpose=False, times: Times | None = None) -> "Tiled":
+        """CSR -> tiled CSR.  Arrays are numpy (host) or integer device pointers (all three alike)."""
+        if not isinstance(row_ptr, (int, np.integer)):
+            row_ptr = np.ascontiguousarray(row_ptr, np.int32); col_idx = np.ascontiguousarray(col_idx, np.int32)
+            vals = np.ascontiguousarray(vals, np.float64)
+        h = C.c_void_p()
+        rc = load().pem_convert_csr(self._h, rows, cols, _ptr(row_ptr), _ptr(col_idx), _ptr(vals), int(bool(transpose)),
+                                    C.byref(h), C.byref(times) if times is not None else None)
         self._check(rc)
         return Tiled(self, h)
 
@@ -327,6 +349,14 @@ class Result:
         v = np.empty(n, np.float64) if values else None
         self.ctx._check(load().pem_result_to_coo(self.ctx._h, self._h, _ptr(r), _ptr(c), _ptr(v)))
         return r, c, v
+
+    def to_csr(self):
+        """(row_ptr int64, cols, vals) on the host, ascending columns inside a row."""
+        i = self.info
+        nrows = max(0, min(i.rows, i.tile_row_end * 16) - i.tile_row_begin * 16)
+        rp = np.empty(nrows + 1, np.int64); c = np.empty(i.nnz, np.int32); v = np.empty(i.nnz, np.float64)
+        self.ctx._check(load().pem_result_to_csr(self.ctx._h, self._h, _ptr(rp), _ptr(c), _ptr(v)))
+        return rp, c, v
 
     def to_coo_into(self, rows_ptr, cols_ptr, vals_ptr):
         """Same, into caller-owned HOST buffers given as integer addresses (pinned memory for full PCIe

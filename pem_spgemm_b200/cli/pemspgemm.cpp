@@ -12,9 +12,11 @@
 //
 // Environment (the positional surface is unchanged): PEM_REPEAT (default 10, Makefile:34),
 // PEM_WARMUP (default 1, spgemm.cu:712-714), PEM_DEVICE (default 0), PEM_DUMP_DIR (default /tmp),
-// PEM_CSV (default ./pemspgemm_benchmark_result.csv), PEM_KEEP_EMPTY=1 for reference-faithful
-// "C tiles" (PEM_OPT_KEEP_EMPTY_TILES), PEM_PANELS=n to multiply in n sequential tile-row panels (a C that does not
+// PEM_CSV (default ./pemspgemm_benchmark_result.csv), PEM_KEEP_EMPTY=1 to carry the reference's empty C'
+// tiles through all three steps (PEM_OPT_KEEP_EMPTY_TILES; "C tiles" is the reference's count either way: it
+// comes from one untimed tile-level symbolic pass), PEM_PANELS=n to multiply in n sequential tile-row panels (a C that does not
 // fit the GPU in tiled form is produced, dumped and freed panel by panel; timings are summed over the panels).
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +34,30 @@ static int env_int(const char* name, int dflt)
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
+
+// One value per line, formatted with to_chars into a large buffer and written in a few fwrite calls (the
+// reference streams one `<<` per line, spgemm.cu:1549-1558, which is slower than the SpGEMM by orders of
+// magnitude).  Doubles: fixed notation, max_digits10 = 17 decimals, the digits `std::fixed <<
+// setprecision(17)` prints.
+struct LineWriter {
+    FILE* f;
+    std::vector<char> buf;
+    size_t n = 0;
+    bool ok;
+    explicit LineWriter(const std::string& path) : f(fopen(path.c_str(), "wb")), buf((size_t)1 << 22), ok(f != nullptr) {}
+    ~LineWriter() { close(); }
+    void flush() { if (f && n) { ok = ok && fwrite(buf.data(), 1, n, f) == n; n = 0; } }
+    char* room(size_t need) { if (n + need > buf.size()) flush(); return buf.data() + n; }
+    void put(int32_t x) { char* p = room(16); auto r = std::to_chars(p, p + 15, x); *r.ptr++ = '\n'; n += (size_t)(r.ptr - p); }
+    void put(double x)
+    {
+        char* p = room(400);
+        auto r = std::to_chars(p, p + 399, x, std::chars_format::fixed, std::numeric_limits<double>::max_digits10);
+        *r.ptr++ = '\n';
+        n += (size_t)(r.ptr - p);
+    }
+    bool close() { flush(); if (f) { ok = ok && fclose(f) == 0; f = nullptr; } return ok; }
+};
 
 #define DIE_IF(rc, ctx, what)                                                              \
     do {                                                                                   \
@@ -111,6 +137,22 @@ int main(int argc, char* argv[])
     std::vector<int32_t> bounds((size_t)PANELS + 1);
     rc = pem_partition_panels(ctx, A, B, PANELS, bounds.data());
     DIE_IF(rc, ctx, "panel split");
+    // "C tiles" as the reference counts them (spgemm.cu:1420): every structurally reachable tile of C',
+    // empty ones included.  One untimed tile-level symbolic pass; the timed products drop empty tiles.
+    int64_t ref_c_tiles = 0;
+    {
+        pem_ctx_set_option(ctx, PEM_OPT_KEEP_EMPTY_TILES, 1);
+        for (int pn = 0; pn < PANELS; ++pn) {
+            pem_result* S = nullptr;
+            rc = pem_step1_symbolic(ctx, A, B, bounds[(size_t)pn], bounds[(size_t)pn + 1], &S);
+            DIE_IF(rc, ctx, "tile-level symbolic pass");
+            pem_result_info si;
+            pem_result_info_get(S, &si);
+            ref_c_tiles += si.tiles;
+            pem_result_free(ctx, S);
+        }
+        pem_ctx_set_option(ctx, PEM_OPT_KEEP_EMPTY_TILES, env_int("PEM_KEEP_EMPTY", 0) ? 1 : 0);
+    }
     pem_result* C = nullptr;                      // the last panel of the last iteration (the whole C when PANELS == 1)
     int64_t c_tiles = 0, c_nnz = 0;
     double s1 = 0, s2 = 0, s3 = 0, total = 0, kernel = 0, mall = 0;
@@ -150,7 +192,7 @@ int main(int argc, char* argv[])
     std::cout << "pemSpGEMM took " << total << "ms ----- GFlops: " << gflops << "\nKernel time " << kernel
               << "ms\nmalloc time " << mall << "ms\n";
     std::cout << "Flop count: " << flop << "\n\n";
-    std::cout << "C tiles: " << ic.tiles << "\n";
+    std::cout << "C tiles: " << ref_c_tiles << " (non-empty: " << ic.tiles << ")\n";
     std::cout << "C nnz: " << ic.nnz << "\n";
     std::cout << "Compression ratio " << compression << "\n";
 
@@ -180,8 +222,7 @@ int main(int argc, char* argv[])
         out.open(dir + "/SPGEMM_RESULT_NNZ.txt");
         out << ic.nnz;                                   // no trailing newline (spgemm.cu:1546)
         out.close();
-        std::ofstream fr(dir + "/SPGEMM_RESULT_ROWS.txt"), fc(dir + "/SPGEMM_RESULT_COLS.txt"), fv(dir + "/SPGEMM_RESULT_VALS.txt");
-        fv << std::fixed << std::setprecision(std::numeric_limits<double>::max_digits10);
+        LineWriter fr(dir + "/SPGEMM_RESULT_ROWS.txt"), fc(dir + "/SPGEMM_RESULT_COLS.txt"), fv(dir + "/SPGEMM_RESULT_VALS.txt");
         for (int pn = 0; pn < PANELS; ++pn) {            // panels in order = rows in order
             if (PANELS > 1) {                             // only the last panel is still alive: recompute the others
                 pem_result_free(ctx, C); C = nullptr;
@@ -194,12 +235,12 @@ int main(int argc, char* argv[])
             std::vector<double> v((size_t)pi.nnz);
             rc = pem_result_to_coo(ctx, C, r.data(), c.data(), v.data());
             DIE_IF(rc, ctx, "COO export");
-            for (auto x : r) fr << x << "\n";
-            for (auto x : c) fc << x << "\n";
-            for (auto x : v) fv << x << "\n";
+            for (auto x : r) fr.put(x);
+            for (auto x : c) fc.put(x);
+            for (auto x : v) fv.put(x);
         }
-        fr.close(); fc.close(); fv.close();
-        if (!fr || !fc || !fv) exit_code = 2;
+        const bool okr = fr.close(), okc = fc.close(), okv = fv.close();
+        if (!okr || !okc || !okv) exit_code = 2;
     }
     std::cout << "CLEANING UP RESOURCES\n\n";
     pem_result_free(ctx, C);

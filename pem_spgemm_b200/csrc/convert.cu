@@ -69,6 +69,20 @@ k_gather_vals(const uint32_t* __restrict__ pos, const double* __restrict__ V, in
     if (e < nnz) vals[e] = V[pos[e]];
 }
 
+// CSR input: row index of nonzero e = last row whose pointer is <= e (binary search; rows of any length)
+__global__ void __launch_bounds__(256)
+k_csr_rows(const int32_t* __restrict__ rp, int rows, int64_t nnz, int32_t* __restrict__ I)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int lo = 0, hi = rows;                      // invariant: rp[lo] <= e < rp[hi]
+    while (hi - lo > 1) {
+        const int mid = (int)(((int64_t)lo + hi) >> 1);
+        if ((int64_t)rp[mid] <= e) lo = mid; else hi = mid;
+    }
+    I[e] = lo;
+}
+
 // predicate for the tile census: position e starts a new tile
 struct HeadPred {
     const uint64_t* keys;
@@ -435,8 +449,19 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     T->rows = rows; T->cols = cols; T->nnz = nnz;
     T->tile_rows = (int32_t)(((int64_t)rows + PEM_TILE - 1) / PEM_TILE);
     T->tile_cols = (int32_t)(((int64_t)cols + PEM_TILE - 1) / PEM_TILE);
+    // every temporary of the conversion, so that one cleanup serves every early return
+    int32_t *dI = nullptr, *dJ = nullptr;
+    double* dV = nullptr;
+    bool own = false;
+    uint64_t *keys = nullptr, *keys_sorted = nullptr;
+    uint32_t *pos = nullptr, *pos_sorted = nullptr, *start_tmp = nullptr;
+    char* tmp = nullptr;
     auto fail = [&](int rc) {
         cudaStreamSynchronize(ctx->copy_stream);    // nothing may still be writing a buffer that goes back to the cache
+        cudaStreamSynchronize(ctx->stream);
+        if (own) { pem_free(ctx, dI); pem_free(ctx, dJ); pem_free(ctx, dV); }
+        pem_free(ctx, keys); pem_free(ctx, keys_sorted); pem_free(ctx, pos); pem_free(ctx, pos_sorted);
+        pem_free(ctx, start_tmp); pem_free(ctx, tmp);
         pem_tiled_free(ctx, T);
         return rc;
     };
@@ -450,9 +475,7 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     if (nnz > 0) {
         int cb = h_bits_for(T->tile_cols), rb = h_bits_for(T->tile_rows);
         // stage the COO on the device if it came from the host (pinned or pageable)
-        int32_t *dI = nullptr, *dJ = nullptr;
-        double* dV = nullptr;
-        bool own = !is_device_ptr(I);
+        own = !is_device_ptr(I);
         if (own) {
             CV_TRY(pem_alloc(ctx, &dI, (size_t)nnz));
             CV_TRY(pem_alloc(ctx, &dJ, (size_t)nnz));
@@ -467,8 +490,6 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         } else {
             dI = const_cast<int32_t*>(I); dJ = const_cast<int32_t*>(J); dV = const_cast<double*>(V);
         }
-        uint64_t *keys = nullptr, *keys_sorted = nullptr;
-        uint32_t *pos = nullptr, *pos_sorted = nullptr;
         CV_TRY(pem_alloc(ctx, &keys, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &keys_sorted, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &pos, (size_t)nnz));
@@ -484,13 +505,11 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         // one radix sort of (key, original position) over the bits in use
         size_t tmp_bytes = 0, tmp2 = 0;
         CV_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, pos, pos_sorted, nnz, 0, 8 + cb + rb, ctx->stream));
-        uint32_t* start_tmp = nullptr;
         CV_TRY(pem_alloc(ctx, &start_tmp, (size_t)nnz + 1));
         cub::CountingInputIterator<uint32_t> iota(0);
         HeadPred pred{keys_sorted};
         int64_t* d_count = ctx->d_scalars + SC_COUNT;
         CV_CK(cub::DeviceSelect::If(nullptr, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
-        char* tmp = nullptr;
         CV_TRY(pem_alloc(ctx, &tmp, std::max(tmp_bytes, tmp2)));
         CV_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, pos, pos_sorted, nnz, 0, 8 + cb + rb, ctx->stream));
         CV_CK(cub::DeviceSelect::If(tmp, tmp2, iota, start_tmp, d_count, nnz, pred, ctx->stream));
@@ -527,15 +546,9 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         // default contract: the caller's arrays are free again when this call returns, so the host waits for the
         // values' upload (not for their gather); PEM_OPT_ASYNC_VALUES hands that wait to the caller
         if (own && !ctx->opt_async_vals) CV_CK(cudaEventSynchronize(ctx->ev_copy[1]));
-        if (ctx->h_scalars[SC_ERR] & 1) {
-            pem_free(ctx, keys_sorted); pem_free(ctx, start_tmp);
-            return fail(ctx->fail(PEM_ERR_RANGE, "COO coordinate outside the matrix"));
-        }
+        if (ctx->h_scalars[SC_ERR] & 1) return fail(ctx->fail(PEM_ERR_RANGE, "COO coordinate outside the matrix"));
         int64_t cnt = ctx->h_scalars[SC_COUNT];
-        if (cnt >= (int64_t(1) << 31) - 1) {
-            pem_free(ctx, keys_sorted); pem_free(ctx, start_tmp);
-            return fail(ctx->fail(PEM_ERR_LIMIT, "more than 2^31 tiles"));
-        }
+        if (cnt >= (int64_t(1) << 31) - 1) return fail(ctx->fail(PEM_ERR_LIMIT, "more than 2^31 tiles"));
         T->tiles = (int32_t)cnt;
         size_t n = (size_t)cnt;
         CV_TRY(pem_alloc(ctx, &T->tile_nnz_ptr, n + 1));
@@ -581,6 +594,62 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     }
     *out = T;
     return PEM_OK;
+}
+
+int pem_convert_csr(pem_ctx* ctx, int32_t rows, int32_t cols, const int32_t* row_ptr, const int32_t* col_idx,
+                    const double* vals, int transpose, pem_tiled** out, pem_times* times)
+{
+    PEM_RANGE("pem_convert_csr");
+    if (!ctx || !out) return PEM_ERR_ARG;
+    *out = nullptr;
+    if (rows < 0 || cols < 0 || !row_ptr) return ctx->fail(PEM_ERR_ARG, "bad CSR arguments");
+    PEM_CK(cudaSetDevice(ctx->device));
+    auto wall0 = std::chrono::high_resolution_clock::now();
+    const bool on_device = is_device_ptr(row_ptr);
+    int32_t first = 0, last = 0;
+    if (on_device) {
+        PEM_CK(cudaMemcpyAsync(&first, row_ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PEM_CK(cudaMemcpyAsync(&last, row_ptr + rows, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PEM_CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        first = row_ptr[0]; last = row_ptr[rows];
+    }
+    if (first != 0 || last < 0) return ctx->fail(PEM_ERR_ARG, "CSR row pointer must start at 0 and be non-negative");
+    const int64_t nnz = last;
+    if (nnz > 0 && (!col_idx || !vals)) return ctx->fail(PEM_ERR_ARG, "null CSR array");
+    // everything onto the device (the row pointer expands to one row index per nonzero there), then the COO path
+    int32_t *d_rp = nullptr, *dI = nullptr, *dJ = nullptr;
+    double* dV = nullptr;
+    auto cleanup = [&]() {
+        pem_free(ctx, dI);
+        if (!on_device) { pem_free(ctx, d_rp); pem_free(ctx, dJ); pem_free(ctx, dV); }
+    };
+    int rc = pem_alloc(ctx, &dI, (size_t)nnz);
+    const int32_t* rp = row_ptr;
+    const int32_t* J = col_idx;
+    const double* V = vals;
+    if (rc == PEM_OK && !on_device) {
+        rc = pem_alloc(ctx, &d_rp, (size_t)rows + 1);
+        if (rc == PEM_OK) rc = pem_alloc(ctx, &dJ, (size_t)nnz);
+        if (rc == PEM_OK) rc = pem_alloc(ctx, &dV, (size_t)nnz);
+        cudaError_t e = cudaSuccess;
+        if (rc == PEM_OK) e = cudaMemcpyAsync(d_rp, row_ptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == PEM_OK && e == cudaSuccess && nnz) e = cudaMemcpyAsync(dJ, col_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == PEM_OK && e == cudaSuccess && nnz) e = cudaMemcpyAsync(dV, vals, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (rc == PEM_OK && e != cudaSuccess) rc = ctx->fail_cuda(e, "upload of the CSR arrays", __FILE__, __LINE__);
+        rp = d_rp; J = dJ; V = dV;
+    }
+    if (rc == PEM_OK && nnz > 0) {
+        k_csr_rows<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(rp, rows, nnz, dI);
+        ++ctx->launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = ctx->fail_cuda(e, "k_csr_rows", __FILE__, __LINE__);
+    }
+    if (rc == PEM_OK) rc = pem_convert_coo(ctx, rows, cols, nnz, dI, J, V, transpose, out, times);
+    cleanup();
+    if (rc == PEM_OK && times)
+        times->convert_total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - wall0).count();
+    return rc;
 }
 
 }  // extern "C"

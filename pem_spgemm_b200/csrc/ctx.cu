@@ -14,15 +14,16 @@
 // ---- caching allocator -----------------------------------------------------------------------
 // Replaces the reference's per-iteration cudaMallocAsync + 11 blocking cudaFree (spgemm.cu:1118-1131,
 // 1138-1295; its malloc_time).  Blocks come from the context's cudaMemPool_t once and are then
-// recycled by size: a block serves a request of up to its own size and no less than half of it
+// recycled by size: a block serves a request of up to its own size and no less than three quarters of it
 // (sequential tile-row panels of one product ask for similar, not equal, sizes).  Cached blocks are
-// only handed back to the driver when an allocation fails or the cache outgrows 80 % of the device:
+// only handed back to the driver when an allocation fails, when the cache outgrows its limit (80 % of the
+// memory that was free when the context was created; PEM_OPT_CACHE_LIMIT_MB) or on pem_ctx_trim:
 // unmapping and re-mapping tens of GB costs seconds, far more than any kernel here.
 int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
 {
     bytes = (bytes + 511) & ~(size_t)511;
     auto it = ctx->free_blocks.lower_bound(bytes);
-    if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 2) {
+    if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 4) {
         *p = it->second;
         ctx->live_blocks[*p] = it->first;
         ctx->cached_bytes -= it->first;
@@ -110,7 +111,7 @@ int pem_ctx_create(pem_ctx** out, int device)
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        ctx->cache_limit = total_b / 5 * 4;
+        ctx->cache_limit = free_b / 5 * 4;      // of what was FREE at creation: other allocators in the process keep theirs
         ctx->free_at_create = free_b;
     }
     *out = ctx;
@@ -154,6 +155,20 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
             if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0..3");
             ctx->opt_owner = (int)value;
             return PEM_OK;
+        case PEM_OPT_TRACE: ctx->opt_trace = (int)value; return PEM_OK;
+        case PEM_OPT_ESC_VARIANT:
+            if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_ESC_VARIANT must be 0..3");
+            ctx->opt_esc_variant = (int)value;
+            return PEM_OK;
+        case PEM_OPT_CACHE_LIMIT_MB:
+            if (value < 0) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_CACHE_LIMIT_MB must be >= 0");
+            ctx->cache_limit = (size_t)value << 20;
+            if (ctx->cached_bytes > ctx->cache_limit) pem_cache_release(ctx);
+            return PEM_OK;
+        case PEM_OPT_STEP2_KERNEL:
+            if (value < 0 || value > 2) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP2_KERNEL must be 0..2");
+            ctx->opt_step2_kernel = (int)value;
+            return PEM_OK;
         case PEM_OPT_ASYNC_VALUES: ctx->opt_async_vals = value != 0; return PEM_OK;
         case PEM_OPT_S3_SMALL_NNZ:
             if (value < 0 || value > 256) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_S3_SMALL_NNZ must be 0..256");
@@ -187,6 +202,14 @@ int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n)
 }
 
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx) { return ctx ? ctx->pool_mallocs : 0; }
+
+int pem_ctx_trim(pem_ctx* ctx)
+{
+    if (!ctx) return PEM_ERR_ARG;
+    PEM_CK(cudaSetDevice(ctx->device));
+    pem_cache_release(ctx);
+    return PEM_OK;
+}
 
 int64_t pem_ctx_pool_bytes(const pem_ctx* ctx)
 {

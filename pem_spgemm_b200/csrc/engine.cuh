@@ -34,6 +34,9 @@ struct pem_ctx {
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
     int opt_owner = 0;           // PEM_OPT_OWNER: 0 / 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel
+    int opt_trace = 0;           // PEM_OPT_TRACE: host-side timeline of step 1 on stderr
+    int opt_esc_variant = 0;     // PEM_OPT_ESC_VARIANT: bit 0 = count-then-write expansion, bit 1 = no block-local row sort
+    int opt_step2_kernel = 0;    // PEM_OPT_STEP2_KERNEL: 0 / 1 = lane per pair, 2 = sixteen lanes per C' tile
     int opt_async_vals = 0;      // PEM_OPT_ASYNC_VALUES: pem_convert_coo returns while the values' upload is still in flight
     int opt_s3_small_e = 8;      // PEM_OPT_S3_SMALL_NNZ: step 3 handles a tile with at most this many nonzeros ...
     int opt_s3_small_np = 64;    // PEM_OPT_S3_SMALL_PAIRS: ... and at most this many pairs with one thread

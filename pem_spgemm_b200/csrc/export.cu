@@ -5,6 +5,7 @@
 // already ordered by tile column and the entries of a tile are row-major, so no sort is needed:
 // 16 lanes (one per row of the tile row) walk the tile row's tiles in order; lane r counts, then
 // places, the entries of matrix row 16*i + r.  The row pointer comes out as a by-product (CSR).
+#include <algorithm>
 #include <vector>
 
 #include "engine.cuh"
@@ -135,6 +136,34 @@ int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t*
         if (e != cudaSuccess) rc = ctx->fail_cuda(e, "D2H copy of the COO result", __FILE__, __LINE__);
     }
     pem_free(ctx, dr); pem_free(ctx, dc); pem_free(ctx, dv);
+    return rc;
+}
+
+int pem_result_to_csr(pem_ctx* ctx, const pem_result* C, int64_t* row_ptr, int32_t* cols, double* vals)
+{
+    PEM_RANGE("pem_result_to_csr");
+    if (!ctx || !C) return PEM_ERR_ARG;
+    const int64_t first_row = (int64_t)C->rb * 16;
+    const int64_t nrows = std::max<int64_t>(0, std::min<int64_t>(C->rows, (int64_t)C->re * 16) - first_row);
+    int32_t* dc = nullptr;
+    double* dv = nullptr;
+    int64_t* drp = nullptr;
+    const size_t n = (size_t)C->nnz;
+    int rc = PEM_OK;
+    if (cols) rc = pem_alloc(ctx, &dc, n);
+    if (vals && rc == PEM_OK) rc = pem_alloc(ctx, &dv, n);
+    if (rc == PEM_OK) rc = pem_alloc(ctx, &drp, (size_t)(C->re - C->rb) * 16 + 1);
+    if (rc == PEM_OK) rc = pem_result_to_coo_device(ctx, C, nullptr, dc, dv, drp);
+    if (rc == PEM_OK) {
+        cudaError_t e = cudaSuccess;
+        // rows past the matrix edge (last tile row) are empty: their pointers equal nnz, so the first nrows + 1 entries are the CSR pointer
+        if (row_ptr) e = cudaMemcpyAsync(row_ptr, drp, ((size_t)nrows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cols && n && e == cudaSuccess) e = cudaMemcpyAsync(cols, dc, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (vals && n && e == cudaSuccess) e = cudaMemcpyAsync(vals, dv, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx->fail_cuda(e, "D2H copy of the CSR result", __FILE__, __LINE__);
+    }
+    pem_free(ctx, dc); pem_free(ctx, dv); pem_free(ctx, drp);
     return rc;
 }
 

@@ -254,6 +254,74 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
     }
 }
 
+// step 2, kernel 1, alternative mapping (PEM_OPT_STEP2_KERNEL = 2; an independent formulation the tests
+// cross-check the pair kernel with): SIXTEEN LANES PER C' TILE, lane = row r, the tile's pairs walked in order.  Per pair the half-warp loads
+// A's 16 row masks and B's 16 row masks with one coalesced 32-byte load each; lane r then ORs B's row k for
+// every k in Arow[r], fetching it from the lane that holds it with a shuffle: no nonzero list, no shared
+// memory, no per-nonzero gather, and the trip count of a pair is the longest A row (3 for a band) instead
+// of the A tile's nonzero count.  The pair's hit word (C rows touched << 16 | C columns touched) comes
+// from one ballot and one OR-reduction; k_hit_transpose turns 32 consecutive hit words into step 3's
+// bit-transposed block afterwards.
+__global__ void __launch_bounds__(256)
+k_step2_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
+              const uint16_t* __restrict__ Amasks, const uint16_t* __restrict__ Bmasks,
+              uint16_t* __restrict__ Cmasks, uint32_t* __restrict__ hit)
+{
+    const int tid = threadIdx.x;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + tid) >> 4;
+    const unsigned r = tid & 15u;
+    if (t >= n_tiles) return;                       // whole 16-lane groups leave together
+    const unsigned sh = tid & 16u;
+    const unsigned grp = 0xFFFFu << sh;
+    const int64_t ps = pair_ptr[t];
+    const unsigned np = (unsigned)(pair_ptr[t + 1] - ps);
+    const int2* __restrict__ pl = pairs + ps;
+    uint32_t* __restrict__ hp = hit + ps;
+    unsigned acc = 0;
+    int2 ab = pl[0];
+    unsigned am = Amasks[(size_t)(unsigned)ab.x * 16u + r], bm = Bmasks[(size_t)(unsigned)ab.y * 16u + r];
+    for (unsigned i = 0; i < np; ++i) {
+        unsigned a = am;
+        const unsigned b = bm;
+        if (i + 1 < np) {                           // next pair's masks while this one is consumed
+            ab = pl[i + 1];
+            am = Amasks[(size_t)(unsigned)ab.x * 16u + r];
+            bm = Bmasks[(size_t)(unsigned)ab.y * 16u + r];
+        }
+        unsigned p = 0;
+        while (__any_sync(grp, a != 0)) {           // uniform over the sixteen lanes: every lane feeds the shuffle
+            const unsigned k = a ? (unsigned)__ffs(a) - 1u : 0u;
+            const unsigned v = __shfl_sync(grp, b, (int)k, 16);
+            p |= a ? v : 0u;
+            a &= a - 1u;
+        }
+        acc |= p;
+        const unsigned rows_hit = (__ballot_sync(grp, p != 0) >> sh) & 0xFFFFu;
+        const unsigned cols_hit = __reduce_or_sync(grp, p);
+        if (r == 0) hp[i] = (rows_hit << 16) | cols_hit;
+    }
+    Cmasks[t * 16 + r] = (uint16_t)acc;
+}
+
+// hit words of 32 consecutive pairs -> one bit-transposed 32-word block, in place (what k_step2_pairs
+// produces directly): afterwards word 16+r (resp. c) of block b has bit i set iff pair 32b+i touches C row
+// r (resp. column c)
+__global__ void __launch_bounds__(256)
+k_hit_transpose(int64_t n_pairs, uint32_t* __restrict__ hit)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
+    if (base >= n_pairs) return;                    // whole warps leave together
+    unsigned v = base + lane < n_pairs ? hit[base + lane] : 0u, m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const unsigned y = __shfl_xor_sync(0xffffffffu, v, j);
+        v = (lane & j) ? ((v & ~m) | ((y >> j) & m)) : ((v & ~(m << j)) | ((y & m) << j));
+        m ^= m << (j >> 1);
+    }
+    hit[base + lane] = v;                           // the array is padded to whole blocks
+}
+
 // per-tile nnz = popcount of the 256-bit mask, fed straight into the exclusive scan
 struct TileNnz {
     const uint4* masks;
@@ -307,8 +375,20 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
         const int64_t nblk = (C->pairs + S2P_THREADS - 1) / S2P_THREADS;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "more than 2^39 tile pairs");
         PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)nblk * S2P_THREADS));
-        PEM_CK(cudaMemsetAsync(C->masks, 0, (size_t)C->tiles * 32, ctx->stream));
-        if (C->pairs > 0) {
+        // one lane per pair by default; sixteen lanes per C' tile (k_step2_tiles) on request: measured on B200 it
+        // loses even on the stencil product it was written for (config 4: 7.1 ms against 3.4 ms)
+        const bool by_tiles = ctx->opt_step2_kernel == 2;
+        if (by_tiles && C->pairs > 0) {
+            pem_free(ctx, C->pair_blk);
+            KT_BEGIN(KT_PAIRS);
+            k_step2_tiles<<<pem_div_up(C->tiles * 16, 256), 256, 0, ctx->stream>>>(
+                C->tiles, C->pair_ptr, C->pair_list, A->masks, B->masks, C->masks, C->pair_hit);
+            PEM_LAUNCHED();
+            k_hit_transpose<<<pem_div_up(C->pairs, 256), 256, 0, ctx->stream>>>(C->pairs, C->pair_hit);
+            KT_END(KT_PAIRS);
+            PEM_LAUNCHED();
+        } else if (C->pairs > 0) {
+            PEM_CK(cudaMemsetAsync(C->masks, 0, (size_t)C->tiles * 32, ctx->stream));
             int32_t* blk = C->pair_blk;            // expand-sort-compress leaves it behind (k_ctiles)
             C->pair_blk = nullptr;
             if (!blk) {
@@ -323,6 +403,8 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
             KT_END(KT_PAIRS);
             PEM_LAUNCHED();
             pem_free(ctx, blk);
+        } else {
+            PEM_CK(cudaMemsetAsync(C->masks, 0, (size_t)C->tiles * 32, ctx->stream));
         }
         // per-tile nnz (popcount of the mask) -> exclusive scan, in one pass over the masks
         auto nnz_it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0),

@@ -634,7 +634,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
         S_TRY(pem_alloc(ctx, &tmp_pq, (size_t)C->pairs));
         S_TRY(pem_alloc(ctx, &tmp_j, (size_t)C->pairs));
     }
-    const bool want_prof = getenv("PEM_PROFILE_STEP1") != nullptr;
+    const bool want_prof = ctx->opt_trace > 1;      // PEM_OPT_TRACE = 2: per-phase cycle counters of the bitmap kernels
     if (want_prof) {
         S_TRY(pem_alloc(ctx, &prof, 16));
         S_CK(cudaMemsetAsync(prof, 0, 16 * 8, ctx->stream));

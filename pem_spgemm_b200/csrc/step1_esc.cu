@@ -46,11 +46,11 @@
 
 namespace {
 
-// PEM_TRACE=1: host-side timeline of step 1 (where the host waits), printed to stderr
+// PEM_OPT_TRACE: host-side timeline of step 1 (where the host waits), printed to stderr
 struct Trace {
     bool on;
     std::chrono::high_resolution_clock::time_point t0;
-    Trace() : on(getenv("PEM_TRACE") != nullptr), t0(std::chrono::high_resolution_clock::now()) {}
+    explicit Trace(bool on_) : on(on_), t0(std::chrono::high_resolution_clock::now()) {}
     void mark(const char* what)
     {
         if (!on) return;
@@ -438,7 +438,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     const int64_t nchunks64 = (total + EX_CHUNK - 1) / EX_CHUNK;
     if (nchunks64 > 0x7ffffff0LL) return ctx->fail(PEM_ERR_LIMIT, "step 1: more than 2^42 tile products");
     const int nchunks = (int)nchunks64;
-    Trace tr;
+    Trace tr(ctx->opt_trace != 0);
     tr.mark("esc_run begin");
     int32_t* split = nullptr;
     int64_t* chunk_off = nullptr;
@@ -465,9 +465,8 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     // free device memory, from the context's own books (cudaMemGetInfo takes ~0.7 ms on a B200 box)
     const size_t free_b = ctx->free_at_create > ctx->pool_taken ? ctx->free_at_create - ctx->pool_taken : 0;
     const size_t staged_bytes = (size_t)P * (sizeof(KeyT) + sizeof(int2));
-    // (PEM_ESC_TWO_PASS=1 forces the count-then-write variant; tests use it, nothing else should)
-    const char* force2 = getenv("PEM_ESC_TWO_PASS");
-    bool staged = !(force2 && *force2 == '1') &&
+    // (PEM_OPT_ESC_VARIANT bit 0 forces the count-then-write variant; tests use it, nothing else should)
+    bool staged = !(ctx->opt_esc_variant & 1) &&
                   staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
     int64_t F = 0;
     if (staged && (pem_alloc(ctx, &key_b, (size_t)P) != PEM_OK || pem_alloc(ctx, &val_b, (size_t)P) != PEM_OK)) {
@@ -517,7 +516,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     // Short rows (banded / stencil matrices) are sorted row by row in shared memory: one pass over the
     // pairs.  Power-law inputs have rows of millions of pairs and keep the global radix sort.
     int by_rows = 0;                        // 1: every row holds <= 1024 pairs
-    if (F < 0x7fffffffLL && wbits + RS_SMALL_BITS <= 32 && !getenv("PEM_ESC_NO_ROWSORT")) {
+    if (F < 0x7fffffffLL && wbits + RS_SMALL_BITS <= 32 && !(ctx->opt_esc_variant & 2)) {
         E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
         E_CK(cudaMemsetAsync(ctx->d_scalars + SC_MAXD, 0, 8, ctx->stream));
         k_row_offsets<KeyT><<<pem_div_up((int64_t)nrows + 1, 256), 256, 0, ctx->stream>>>(nrows, (int)F, wbits, key_a, seg_off);

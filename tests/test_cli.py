@@ -60,6 +60,14 @@ def test_cli_report_csv_and_dump(tmp_path, aat):
     v = np.loadtxt(tmp_path / "SPGEMM_RESULT_VALS.txt", dtype=np.float64, ndmin=1)
     assert np.array_equal(r, ro) and np.array_equal(c, co)
     np.testing.assert_allclose(v, vo, rtol=1e-12, atol=1e-16)   # std::fixed, 17 decimals
+    # the text itself is what `std::fixed << setprecision(max_digits10)` prints (spgemm.cu:1555-1558)
+    lines = open(tmp_path / "SPGEMM_RESULT_VALS.txt").read().split("\n")
+    assert lines[-1] == "" and lines[:-1] == ["%.17f" % x for x in vo]
+    # "C tiles" is the reference's count: every structurally reachable tile, empty ones included (spgemm.cu:1420)
+    from oracle import tiles as otiles
+    P = otiles.tiled_product(otiles.tile_format(rows, cols, I, J, V), otiles.tile_format(rows, cols, I, J, V, transpose=aat),
+                             keep_empty=True)
+    assert f"C tiles: {P.c_tile_col.size} " in out.stdout
     # CSV (spgemm.cu:1424-1450, README.md:51-53): one row, preceded by a newline, 14 fields, no header
     raw = open(tmp_path / "pemspgemm_benchmark_result.csv").read()
     assert raw.startswith("\n") and raw.count("\n") == 1
@@ -78,6 +86,42 @@ def test_cli_report_csv_and_dump(tmp_path, aat):
     out = _run([mtx, "0"] + (["1"] if aat else []), tmp_path, env)      # second run appends
     assert out.returncode == 0 and "Not saving results. Exiting." in out.stdout
     assert open(tmp_path / "pemspgemm_benchmark_result.csv").read().count("\n") == 2
+
+
+@pytest.mark.gpu
+def test_cli_symmetric_file_is_expanded_with_the_diagonal_once(tmp_path):
+    """A `symmetric` Matrix Market file holds the lower triangle; the reader expands it to general form and
+    emits each diagonal entry ONCE.  (fast_matrix_market v1.7.6, which the reference links, would by default add
+    an extra zero-valued (i,i) duplicate per diagonal entry - duplicates are undefined behaviour in the
+    reference, spgemm.cu:186-191 - so this engine's printed Nnz differs from the reference's for such files;
+    DESIGN.md section 8 and INTEGRATION.md list the deviation.)"""
+    from oracle import host
+    n = 40
+    rng = np.random.default_rng(4)
+    I = rng.integers(0, n, 300); J = rng.integers(0, n, 300)
+    lo = np.unique(np.stack([np.maximum(I, J), np.minimum(I, J)], 1), axis=0)        # lower triangle incl. diagonal
+    V = rng.uniform(-1, 1, len(lo))
+    mtx = str(tmp_path / "sym.mtx")
+    with open(mtx, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real symmetric\n")
+        f.write(f"{n} {n} {len(lo)}\n")
+        for (i, j), v in zip(lo, V):
+            f.write(f"{i + 1} {j + 1} {float(v)!r}\n")
+    off = lo[:, 0] != lo[:, 1]
+    gI = np.concatenate([lo[:, 0], lo[off, 1]]).astype(np.int32); gJ = np.concatenate([lo[:, 1], lo[off, 0]]).astype(np.int32)
+    gV = np.concatenate([V, V[off]])
+    rows, cols, rI, rJ, rV, sym = pem.mtx_read(mtx)
+    assert sym and rI.size == gI.size
+    out = _run([mtx, "1"], tmp_path, {"PEM_DUMP_DIR": str(tmp_path), "PEM_REPEAT": "1", "PEM_WARMUP": "0"})
+    assert out.returncode == 0, out.stderr
+    assert f"Nnz: {gI.size}" in out.stdout
+    _, _, oC = host.spgemm_from_coo(n, n, gI, gJ, gV, False)
+    ro, co, vo = oC.to_coo()
+    r = np.loadtxt(tmp_path / "SPGEMM_RESULT_ROWS.txt", dtype=np.int64, ndmin=1)
+    c = np.loadtxt(tmp_path / "SPGEMM_RESULT_COLS.txt", dtype=np.int64, ndmin=1)
+    v = np.loadtxt(tmp_path / "SPGEMM_RESULT_VALS.txt", dtype=np.float64, ndmin=1)
+    assert np.array_equal(r, ro) and np.array_equal(c, co)
+    np.testing.assert_allclose(v, vo, rtol=1e-12, atol=1e-16)
 
 
 @pytest.mark.gpu

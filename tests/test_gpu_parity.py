@@ -87,6 +87,37 @@ def test_device_transpose_equals_transposed_conversion(engine, shape, nnz, seed)
     T.free(); A.free()
 
 
+@pytest.mark.parametrize("shape,nnz,seed", SHAPES + [((40, 40), 0, 3)])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_csr_in_and_csr_out(engine, shape, nnz, seed, where):
+    """pem_convert_csr must build the same tiled arrays as the COO path, and pem_result_to_csr must return the
+    oracle's CSR of C = A*A^T (row pointer, ascending columns, value bits)."""
+    import torch
+    rows, cols, I, J, V = synth.random_sparse(*shape, nnz, seed=seed)
+    oA = host.coo_to_csr(rows, cols, I, J, V)
+    rp = oA.ptr.astype(np.int32)
+    rng = np.random.default_rng(seed)
+    cj, cv = oA.idx.copy(), oA.val.copy()
+    for r in range(rows):                                   # columns need not be sorted inside a row
+        b, e = rp[r], rp[r + 1]
+        p = rng.permutation(e - b)
+        cj[b:e], cv[b:e] = cj[b:e][p], cv[b:e][p]
+    if where == "device":
+        keep = [torch.from_numpy(x).cuda() for x in (rp, cj, cv)]
+        torch.cuda.synchronize()
+        A = engine.convert_csr(rows, cols, *(t.data_ptr() for t in keep))
+    else:
+        A = engine.convert_csr(rows, cols, rp, cj, cv)
+    _check_tiled(A, tiles.tile_format(rows, cols, I, J, V))
+    T = engine.convert_csr(rows, cols, rp, cj, cv, transpose=True)
+    _check_tiled(T, tiles.tile_format(rows, cols, I, J, V, transpose=True))
+    C = engine.spgemm(A, T)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, True)
+    crp, cc, cvv = C.to_csr()
+    assert np.array_equal(crp, oC.ptr) and np.array_equal(cc, oC.idx) and np.array_equal(cvv, oC.val)
+    C.free(); T.free(); A.free()
+
+
 def test_conversion_dense_tile_and_empty(engine):
     I, J = np.divmod(np.arange(256, dtype=np.int32), 16)
     V = np.arange(256, dtype=np.float64)
@@ -287,6 +318,37 @@ def test_owner_variants_are_bit_identical(engine, k, owner):
     C0.free(); C1.free(); A.free(); B.free()
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("keep_empty", [0, 1])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_step2_kernels_match_tile_oracle(engine, k, keep_empty, kernel):
+    """Both step-2 mask kernels (lane per pair; sixteen lanes per C' tile) against the numpy restatement of
+    compute_CMasksAndOffsets (spgemm.cu:499-550), and the values that step 3 derives from their hit blocks."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep_empty)
+    engine.set_option(pem.OPT_STEP2_KERNEL, kernel)
+    try:
+        A = engine.convert_coo(rows, cols, I, J, V)
+        B = engine.transpose(A) if tb else A
+        OA = tiles.tile_format(rows, cols, I, J, V)
+        OB = tiles.tile_format(rows, cols, I, J, V, transpose=tb)
+        P = tiles.tiled_product(OA, OB, keep_empty=bool(keep_empty))
+        C = engine.step1(A, B)
+        engine.step2(A, B, C)
+        assert np.array_equal(C.array("masks").reshape(-1, 16), P.c_masks)
+        assert np.array_equal(C.array("tile_nnz_ptr"), P.c_tile_nnz_ptr)
+        engine.step3(A, B, C)
+        _, _, Co = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+        _assert_same_C(C, Co)
+        C.free()
+        if B is not A:
+            B.free()
+        A.free()
+    finally:
+        engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+        engine.set_option(pem.OPT_STEP2_KERNEL, 0)
+
+
 @pytest.mark.parametrize("small_e,small_np", [(0, 0), (256, 1 << 20), (256, 1), (2, 4), (8, 0)])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_step3_tile_classes_are_bit_identical(engine, k, small_e, small_np):
@@ -367,31 +429,30 @@ def test_wide_index_space_uses_64bit_sort_keys(engine):
 @pytest.mark.parametrize("k", [2, 4])
 def test_esc_count_then_write_variant(engine, k):
     """The variant of expand-sort-compress used when product-sized staging buffers would not fit
-    (count per chunk, scan, write exactly): same arrays as the staged variant."""
-    import os
+    (count per chunk, scan, write exactly): same arrays as the staged variant; with and without the
+    block-local row sort (PEM_OPT_ESC_VARIANT bits)."""
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
     A = engine.convert_coo(rows, cols, I, J, V)
     got = {}
-    for two_pass in ("0", "1"):
-        for no_rowsort in ("", "1"):            # block-local row sort (short rows) vs. global radix sort
-            os.environ["PEM_ESC_TWO_PASS"] = two_pass
-            if no_rowsort:
-                os.environ["PEM_ESC_NO_ROWSORT"] = "1"
-            try:
-                for path in (3, 4):
-                    engine.set_option(pem.OPT_STEP1_PATH, path)
-                    C = engine.spgemm(A, A)
-                    got[(two_pass + no_rowsort, path)] = [C.array(x) for x in ("row_ptr", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "vals")]
-                    C.free()
-            finally:
-                os.environ.pop("PEM_ESC_TWO_PASS", None)
-                os.environ.pop("PEM_ESC_NO_ROWSORT", None)
-                engine.set_option(pem.OPT_STEP1_PATH, 0)
-    ref = got[("0", 3)]
+    try:
+        for variant in (0, 1, 2, 3):
+            engine.set_option(pem.OPT_ESC_VARIANT, variant)
+            for path in (3, 4):
+                engine.set_option(pem.OPT_STEP1_PATH, path)
+                C = engine.spgemm(A, A)
+                got[(variant, path)] = [C.array(x) for x in ("row_ptr", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "vals")]
+                C.free()
+    finally:
+        engine.set_option(pem.OPT_ESC_VARIANT, 0)
+        engine.set_option(pem.OPT_STEP1_PATH, 0)
+    ref = got[(0, 3)]
     for key, arrs in got.items():
         for a, b in zip(ref, arrs):
             assert np.array_equal(a, b), key
+    pool = engine.pool_bytes
     A.free()
+    engine.trim()                               # cached blocks go back to the driver
+    assert engine.pool_bytes <= pool
 
 
 def test_config2_full_size_matches_oracle(engine):
@@ -520,6 +581,7 @@ def test_fuzz_all_variants_against_oracle(engine):
         path = (1, 3, 4)[case % 3]
         owner = (2, 0, 1, 3)[case % 4]
         keep = case % 2
+        engine.set_option(pem.OPT_STEP2_KERNEL, (1, 2, 0)[case % 3])
         engine.set_option(pem.OPT_STEP1_PATH, path)
         engine.set_option(pem.OPT_OWNER, owner)
         engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep)
@@ -535,6 +597,7 @@ def test_fuzz_all_variants_against_oracle(engine):
             engine.set_option(pem.OPT_STEP1_PATH, 0)
             engine.set_option(pem.OPT_OWNER, 0)
             engine.set_option(pem.OPT_KEEP_EMPTY_TILES, 0)
+            engine.set_option(pem.OPT_STEP2_KERNEL, 0)
         r = np.concatenate([x[0] for x in parts]); c = np.concatenate([x[1] for x in parts])
         v = np.concatenate([x[2] for x in parts])
         tag = f"case {case}: {m}x{n} nnz {I.size} aat {aat} path {path} owner {owner} keep {keep} parts {nparts}"

@@ -154,6 +154,17 @@ int pem_ctx_trim(pem_ctx* ctx);
 int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
                     const int32_t* I, const int32_t* J, const double* V, int transpose,
                     pem_tiled** out, pem_times* times);
+/* The fp32 instantiation (the reference's kernels are templates over ValueType, spgemm.cu:137,593,727-728, and
+ * ship as double only): same conversion with float values.  A product of two fp32 operands accumulates with
+ * single-precision fma in the same ascending-k order and yields an fp32 result (pem_result_to_coo_f32;
+ * pem_result_get(PEM_R_VALS) and pem_tiled_get(PEM_T_VALS) then move 4-byte values).  Operands of different
+ * value types cannot be multiplied.  fp32 runs the default kernels (PEM_OPT_OWNER 0 / 2). */
+int pem_convert_coo_f32(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
+                        const int32_t* I, const int32_t* J, const float* V, int transpose,
+                        pem_tiled** out, pem_times* times);
+/* 0 = fp64, 1 = fp32 */
+int pem_tiled_dtype(const pem_tiled* t);
+int pem_result_dtype(const pem_result* C);
 /* Same from CSR (the reference builds a CSR on its way to tiles, spgemm.cu:894-928; SURVEY.md section 8f rank 4
  * asks for a CSR-in entry): row_ptr[rows+1] (int32, starts at 0), col_idx / vals [row_ptr[rows]], all three host or
  * all three device pointers; columns need not be sorted inside a row; duplicates are rejected. */
@@ -236,6 +247,7 @@ const void* pem_result_device_ptr(const pem_result* C, int which);
 /* Tiled C -> COO sorted by (row, col): sanitize_C + stable_sort + D2H (spgemm.cu:1493-1543).
  * rows/cols/vals are HOST buffers of pem_result_info.nnz entries (any may be NULL to skip). */
 int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, double* vals);
+int pem_result_to_coo_f32(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, float* vals);
 /* Tiled C -> CSR with ascending columns: row_ptr is a HOST buffer of (rows covered by the result) + 1 int64 entries
  * (the whole C: rows + 1), cols / vals HOST buffers of nnz entries (any may be NULL to skip). */
 int pem_result_to_csr(pem_ctx* ctx, const pem_result* C, int64_t* row_ptr, int32_t* cols, double* vals);

@@ -147,4 +147,36 @@ void oracle_spgemm_numeric(int m, int n, const int64_t* Ap, const int* Aj, const
     }
 }
 
+// fp32 instantiation of the numeric pass (the reference's kernels are templates over ValueType,
+// spgemm.cu:593,727-728): same order, single-precision fma.
+void oracle_spgemm_numeric_f32(int m, int n, const int64_t* Ap, const int* Aj, const float* Ax,
+                               const int64_t* Bp, const int* Bj, const float* Bx,
+                               const int64_t* Cp, int* Cj, float* Cx)
+{
+#pragma omp parallel
+    {
+        std::vector<int> mark((size_t)n, -1);
+        std::vector<float> acc((size_t)n, 0.0f);
+#pragma omp for schedule(dynamic, 256)
+        for (int i = 0; i < m; ++i) {
+            int64_t base = Cp[i], cnt = 0;
+            for (int64_t p = Ap[i]; p < Ap[i + 1]; ++p) {
+                int k = Aj[p];
+                float a = Ax[p];
+                for (int64_t q = Bp[k]; q < Bp[k + 1]; ++q) {
+                    int j = Bj[q];
+                    if (mark[(size_t)j] != i) {
+                        mark[(size_t)j] = i;
+                        acc[(size_t)j] = 0.0f;
+                        Cj[base + cnt++] = j;
+                    }
+                    acc[(size_t)j] = std::fmaf(a, Bx[q], acc[(size_t)j]);
+                }
+            }
+            std::sort(Cj + base, Cj + base + cnt);
+            for (int64_t t = 0; t < cnt; ++t) Cx[base + t] = acc[(size_t)Cj[base + t]];
+        }
+    }
+}
+
 }  // extern "C"

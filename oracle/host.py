@@ -48,6 +48,10 @@ def lib():
         L.oracle_spgemm_numeric.restype = None
         L.oracle_spgemm_numeric.argtypes = [C.c_int, C.c_int, _i64p, _i32p, _f64p, _i64p, _i32p, _f64p,
                                             _i64p, _i32p, _f64p]
+        _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        L.oracle_spgemm_numeric_f32.restype = None
+        L.oracle_spgemm_numeric_f32.argtypes = [C.c_int, C.c_int, _i64p, _i32p, _f32p, _i64p, _i32p, _f32p,
+                                                _i64p, _i32p, _f32p]
         _lib = L
     return _lib
 
@@ -118,6 +122,17 @@ def spgemm(A: CSR, B: CSR, timing: dict | None = None) -> CSR:
     if timing is not None:
         timing["seconds"] = time.perf_counter() - t0
         timing["threads"] = int(lib().oracle_max_threads())
+    return CSR(A.rows, B.cols, cp, cj, cx)
+
+
+def spgemm_f32(A: CSR, B: CSR) -> CSR:
+    """The fp32 instantiation: values rounded to float32 first, single-precision fma in ascending k."""
+    assert A.cols == B.rows
+    cp = np.zeros(A.rows + 1, np.int64)
+    nnz = lib().oracle_spgemm_symbolic(A.rows, B.cols, A.ptr, A.idx, B.ptr, B.idx, cp)
+    cj = np.empty(nnz, np.int32); cx = np.empty(nnz, np.float32)
+    lib().oracle_spgemm_numeric_f32(A.rows, B.cols, A.ptr, A.idx, np.ascontiguousarray(A.val, np.float32),
+                                    B.ptr, B.idx, np.ascontiguousarray(B.val, np.float32), cp, cj, cx)
     return CSR(A.rows, B.cols, cp, cj, cx)
 
 

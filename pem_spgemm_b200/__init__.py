@@ -76,12 +76,12 @@ class ResultInfo(C.Structure):
 
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
-    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_ctx_trim", "pem_convert_coo", "pem_convert_csr", "pem_tiled_transpose",
+    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_pool_bytes", "pem_ctx_trim", "pem_convert_coo", "pem_convert_coo_f32", "pem_tiled_dtype", "pem_result_dtype", "pem_convert_csr", "pem_tiled_transpose",
     "pem_tiled_info_get", "pem_tiled_values_ready",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
     "pem_result_info_get", "pem_result_free", "pem_result_get", "pem_result_device_ptr",
-    "pem_result_to_coo", "pem_result_to_csr", "pem_result_to_coo_device", "pem_result_checksum", "pem_mtx_read", "pem_mtx_write",
+    "pem_result_to_coo", "pem_result_to_coo_f32", "pem_result_to_csr", "pem_result_to_coo_device", "pem_result_checksum", "pem_mtx_read", "pem_mtx_write",
     "pem_free_host",
 ]
 
@@ -118,6 +118,10 @@ def load():
         "pem_ctx_pool_mallocs": (i64, [vp]),
         "pem_ctx_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
         "pem_convert_coo": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
+        "pem_convert_coo_f32": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
+        "pem_tiled_dtype": (C.c_int, [vp]),
+        "pem_result_dtype": (C.c_int, [vp]),
+        "pem_result_to_coo_f32": (C.c_int, [vp, vp, vp, vp, vp]),
         "pem_convert_csr": (C.c_int, [vp, i32, i32, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
         "pem_tiled_transpose": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "pem_tiled_info_get": (C.c_int, [vp, C.POINTER(TiledInfo)]),
@@ -226,17 +230,20 @@ class Context:
         return int(load().pem_ctx_pool_bytes(self._h))
 
     # -- conversion -----------------------------------------------------------------------
-    def convert_coo(self, rows, cols, I, J, V, transpose=False, nnz=None, times: Times | None = None) -> "Tiled":
+    def convert_coo(self, rows, cols, I, J, V, transpose=False, nnz=None, times: Times | None = None,
+                    dtype=np.float64) -> "Tiled":
         """COO -> tiled CSR.  I/J/V are numpy arrays (host) or integer device pointers
-        (then ``nnz`` is required)."""
+        (then ``nnz`` is required).  ``dtype`` float64 (default) or float32 selects the value type."""
+        f32 = np.dtype(dtype) == np.float32
         if not isinstance(I, (int, np.integer)):
             I = np.ascontiguousarray(I, np.int32); J = np.ascontiguousarray(J, np.int32)
-            V = np.ascontiguousarray(V, np.float64)
+            V = np.ascontiguousarray(V, np.float32 if f32 else np.float64)
             nnz = I.size
         h = C.c_void_p()
         self._keep = (I, J, V)
-        rc = load().pem_convert_coo(self._h, rows, cols, nnz, _ptr(I), _ptr(J), _ptr(V), int(bool(transpose)),
-                                    C.byref(h), C.byref(times) if times is not None else None)
+        fn = load().pem_convert_coo_f32 if f32 else load().pem_convert_coo
+        rc = fn(self._h, rows, cols, nnz, _ptr(I), _ptr(J), _ptr(V), int(bool(transpose)),
+                C.byref(h), C.byref(times) if times is not None else None)
         self._keep = None
         self._check(rc)
         return Tiled(self, h)
@@ -302,8 +309,14 @@ class Tiled:
         load().pem_tiled_info_get(self._h, C.byref(i))
         return i
 
+    @property
+    def dtype(self):
+        return np.float32 if load().pem_tiled_dtype(self._h) == 1 else np.float64
+
     def array(self, name: str) -> np.ndarray:
         idx, dt = T_ARRAYS[name]
+        if name == "vals":
+            dt = self.dtype
         i = self.info
         n = {"vals": i.nnz, "tile_nnz_ptr": i.tiles + 1, "masks": i.tiles * 16, "row_ptr": i.tiles * 16,
              "masks_t": i.tiles * 16, "tile_row_ptr": i.tile_rows + 1, "tile_col_idx": i.tiles,
@@ -332,8 +345,14 @@ class Result:
         load().pem_result_info_get(self._h, C.byref(i))
         return i
 
+    @property
+    def dtype(self):
+        return np.float32 if load().pem_result_dtype(self._h) == 1 else np.float64
+
     def array(self, name: str) -> np.ndarray:
         idx, dt = R_ARRAYS[name]
+        if name == "vals":
+            dt = self.dtype
         i = self.info
         n = {"row_ptr": i.tile_row_end - i.tile_row_begin + 1, "tile_row": i.tiles, "tile_col": i.tiles,
              "pair_ptr": i.tiles + 1, "pairs_a": i.pairs, "pairs_b": i.pairs, "masks": i.tiles * 16,
@@ -346,8 +365,10 @@ class Result:
         """(rows, cols, vals) on the host, sorted by (row, col)."""
         n = self.info.nnz
         r = np.empty(n, np.int32); c = np.empty(n, np.int32)
-        v = np.empty(n, np.float64) if values else None
-        self.ctx._check(load().pem_result_to_coo(self.ctx._h, self._h, _ptr(r), _ptr(c), _ptr(v)))
+        f32 = self.dtype == np.float32
+        v = np.empty(n, self.dtype) if values else None
+        fn = load().pem_result_to_coo_f32 if f32 else load().pem_result_to_coo
+        self.ctx._check(fn(self.ctx._h, self._h, _ptr(r), _ptr(c), _ptr(v)))
         return r, c, v
 
     def to_csr(self):

@@ -62,8 +62,9 @@ k_rc_idx(const uint64_t* __restrict__ keys, int64_t nnz, uint8_t* __restrict__ r
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nnz) rc[e] = (uint8_t)(keys[e] & 255u);
 }
+template <class T>
 __global__ void __launch_bounds__(256)
-k_gather_vals(const uint32_t* __restrict__ pos, const double* __restrict__ V, int64_t nnz, double* __restrict__ vals)
+k_gather_vals(const uint32_t* __restrict__ pos, const T* __restrict__ V, int64_t nnz, T* __restrict__ vals)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nnz) vals[e] = V[pos[e]];
@@ -258,10 +259,11 @@ k_row_rec(const uint16_t* __restrict__ masks, const uint8_t* __restrict__ row_pt
 }
 
 // thread per tile: column pointers from the column masks, then every value goes to its column-major slot
+template <class T>
 __global__ void __launch_bounds__(128)
 k_col_views(int cnt, const uint32_t* __restrict__ tile_nnz_ptr, const uint16_t* __restrict__ masks_t,
-            const uint8_t* __restrict__ rc_idx, const double* __restrict__ vals,
-            uint32_t* __restrict__ col_rec, double* __restrict__ vals_t)
+            const uint8_t* __restrict__ rc_idx, const T* __restrict__ vals,
+            uint32_t* __restrict__ col_rec, T* __restrict__ vals_t)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
@@ -335,16 +337,17 @@ k_transpose_counts(const int32_t* __restrict__ perm, const uint32_t* __restrict_
 }
 
 // thread per tile of the transpose: masks swap roles, values move to their column-major position
+template <class T>
 __global__ void __launch_bounds__(128)
 k_transpose_tiles(int cnt, int tile_rows_new, const int32_t* __restrict__ perm, const int64_t* __restrict__ new_ptr,
                   const uint32_t* __restrict__ o_nnz_ptr, const uint16_t* __restrict__ o_masks,
                   const uint16_t* __restrict__ o_masks_t, const int32_t* __restrict__ o_row, const int32_t* __restrict__ o_col,
                   const uint16_t* __restrict__ o_col_occ, const uint16_t* __restrict__ o_row_occ,
-                  const uint8_t* __restrict__ o_rc, const double* __restrict__ o_vals,
+                  const uint8_t* __restrict__ o_rc, const T* __restrict__ o_vals,
                   uint32_t* __restrict__ n_nnz_ptr, uint16_t* __restrict__ n_masks, uint16_t* __restrict__ n_masks_t,
                   uint8_t* __restrict__ n_row_ptr, int32_t* __restrict__ n_row, int32_t* __restrict__ n_col,
                   int32_t* __restrict__ n_tile_row_ptr, uint16_t* __restrict__ n_col_occ, uint16_t* __restrict__ n_row_occ,
-                  uint8_t* __restrict__ n_rc, double* __restrict__ n_vals)
+                  uint8_t* __restrict__ n_rc, T* __restrict__ n_vals)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
@@ -429,13 +432,13 @@ int tile_row_flops(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, unsigne
 
 }  // namespace
 
-extern "C" {
-
-int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
-                    const int32_t* I, const int32_t* J, const double* V, int transpose,
-                    pem_tiled** out, pem_times* times)
+// COO -> tiled CSR for either value type (V points at doubles or floats according to dtype)
+static int convert_coo_any(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
+                           const int32_t* I, const int32_t* J, const void* V, int dtype, int transpose,
+                           pem_tiled** out, pem_times* times)
 {
     PEM_RANGE("pem_convert_coo");
+    const size_t vsz = pem_vsize(dtype);
     if (!ctx || !out) return PEM_ERR_ARG;
     *out = nullptr;
     if (rows < 0 || cols < 0 || nnz < 0) return ctx->fail(PEM_ERR_ARG, "negative size");
@@ -446,12 +449,13 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     if (transpose) { int32_t t = rows; rows = cols; cols = t; }
 
     pem_tiled* T = new pem_tiled();
+    T->dtype = dtype;
     T->rows = rows; T->cols = cols; T->nnz = nnz;
     T->tile_rows = (int32_t)(((int64_t)rows + PEM_TILE - 1) / PEM_TILE);
     T->tile_cols = (int32_t)(((int64_t)cols + PEM_TILE - 1) / PEM_TILE);
     // every temporary of the conversion, so that one cleanup serves every early return
     int32_t *dI = nullptr, *dJ = nullptr;
-    double* dV = nullptr;
+    char* dV = nullptr;
     bool own = false;
     uint64_t *keys = nullptr, *keys_sorted = nullptr;
     uint32_t *pos = nullptr, *pos_sorted = nullptr, *start_tmp = nullptr;
@@ -479,22 +483,22 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
         if (own) {
             CV_TRY(pem_alloc(ctx, &dI, (size_t)nnz));
             CV_TRY(pem_alloc(ctx, &dJ, (size_t)nnz));
-            CV_TRY(pem_alloc(ctx, &dV, (size_t)nnz));
+            CV_TRY(pem_alloc(ctx, &dV, (size_t)nnz * vsz));
             CV_CK(cudaMemcpyAsync(dI, I, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
             CV_CK(cudaMemcpyAsync(dJ, J, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
             // the values travel on a second stream, behind the coordinates and under key generation + sort
             CV_CK(cudaEventRecord(ctx->ev_copy[0], ctx->stream));
             CV_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
-            CV_CK(cudaMemcpyAsync(dV, V, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CV_CK(cudaMemcpyAsync(dV, V, (size_t)nnz * vsz, cudaMemcpyHostToDevice, ctx->copy_stream));
             CV_CK(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
         } else {
-            dI = const_cast<int32_t*>(I); dJ = const_cast<int32_t*>(J); dV = const_cast<double*>(V);
+            dI = const_cast<int32_t*>(I); dJ = const_cast<int32_t*>(J); dV = const_cast<char*>(static_cast<const char*>(V));
         }
         CV_TRY(pem_alloc(ctx, &keys, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &keys_sorted, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &pos, (size_t)nnz));
         CV_TRY(pem_alloc(ctx, &pos_sorted, (size_t)nnz));
-        CV_TRY(pem_alloc(ctx, &T->vals, (size_t)nnz));
+        CV_TRY(pem_alloc_bytes(ctx, (void**)&T->vals, (size_t)nnz * vsz));
         CV_CK(cudaMemsetAsync(ctx->d_scalars, 0, PEM_NSCALARS * sizeof(int64_t), ctx->stream));
 
         int grid = (int)std::min<int64_t>(pem_div_up(nnz, 256), (int64_t)ctx->sm_count * 32);
@@ -524,7 +528,10 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
             CV_CK(cudaEventCreateWithFlags(&T->ev_vals, cudaEventDisableTiming));
             CV_CK(cudaEventRecord(ctx->ev_copy[0], ctx->stream));                  // sorted positions are final
             CV_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[0], 0));
-            k_gather_vals<<<pem_div_up(nnz, 256), 256, 0, ctx->copy_stream>>>(pos_sorted, dV, nnz, T->vals);
+            if (dtype == PEM_F32)
+                k_gather_vals<float><<<pem_div_up(nnz, 256), 256, 0, ctx->copy_stream>>>(pos_sorted, reinterpret_cast<const float*>(dV), nnz, reinterpret_cast<float*>(T->vals));
+            else
+                k_gather_vals<double><<<pem_div_up(nnz, 256), 256, 0, ctx->copy_stream>>>(pos_sorted, reinterpret_cast<const double*>(dV), nnz, T->vals);
             ++ctx->launches;
             CV_CK(cudaGetLastError());
             CV_CK(cudaEventRecord(T->ev_vals, ctx->copy_stream));
@@ -532,7 +539,10 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
             T->pend_buf[0] = pos_sorted; T->pend_buf[1] = dV;                      // freed once the gather is known to be done
             pos_sorted = nullptr; dV = nullptr;
         } else {
-            k_gather_vals<<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(pos_sorted, dV, nnz, T->vals);
+            if (dtype == PEM_F32)
+                k_gather_vals<float><<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(pos_sorted, reinterpret_cast<const float*>(dV), nnz, reinterpret_cast<float*>(T->vals));
+            else
+                k_gather_vals<double><<<pem_div_up(nnz, 256), 256, 0, ctx->stream>>>(pos_sorted, reinterpret_cast<const double*>(dV), nnz, T->vals);
             ++ctx->launches;
             CV_CK(cudaGetLastError());
         }
@@ -594,6 +604,22 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
     }
     *out = T;
     return PEM_OK;
+}
+
+extern "C" {
+
+int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
+                    const int32_t* I, const int32_t* J, const double* V, int transpose,
+                    pem_tiled** out, pem_times* times)
+{
+    return convert_coo_any(ctx, rows, cols, nnz, I, J, V, PEM_F64, transpose, out, times);
+}
+
+int pem_convert_coo_f32(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
+                        const int32_t* I, const int32_t* J, const float* V, int transpose,
+                        pem_tiled** out, pem_times* times)
+{
+    return convert_coo_any(ctx, rows, cols, nnz, I, J, V, PEM_F32, transpose, out, times);
 }
 
 int pem_convert_csr(pem_ctx* ctx, int32_t rows, int32_t cols, const int32_t* row_ptr, const int32_t* col_idx,
@@ -721,10 +747,14 @@ int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* Tc, bool as_a, bool as_
         uint32_t* rec = nullptr;
         double* vt = nullptr;
         PEM_TRY(pem_alloc(ctx, &rec, n16));
-        PEM_TRY(pem_alloc(ctx, &vt, (size_t)T->nnz));
+        PEM_TRY(pem_alloc_bytes(ctx, (void**)&vt, std::max<size_t>(1, (size_t)T->nnz * pem_vsize(T->dtype))));
         if (T->tiles) {
-            k_col_views<<<pem_div_up(T->tiles, 128), 128, 0, ctx->stream>>>(T->tiles, T->tile_nnz_ptr, T->masks_t, T->rc_idx,
-                                                                           T->vals, rec, vt);
+            if (T->dtype == PEM_F32)
+                k_col_views<float><<<pem_div_up(T->tiles, 128), 128, 0, ctx->stream>>>(
+                    T->tiles, T->tile_nnz_ptr, T->masks_t, T->rc_idx, reinterpret_cast<const float*>(T->vals), rec, reinterpret_cast<float*>(vt));
+            else
+                k_col_views<double><<<pem_div_up(T->tiles, 128), 128, 0, ctx->stream>>>(T->tiles, T->tile_nnz_ptr, T->masks_t, T->rc_idx,
+                                                                                       T->vals, rec, vt);
             PEM_LAUNCHED();
         }
         T->col_rec = rec;
@@ -743,6 +773,7 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_tiled_wait_vals(ctx, A));
     pem_tiled* T = new pem_tiled();
+    T->dtype = A->dtype;
     T->rows = A->cols; T->cols = A->rows; T->nnz = A->nnz;
     T->tile_rows = A->tile_cols; T->tile_cols = A->tile_rows; T->tiles = A->tiles;
     const size_t n = (size_t)A->tiles;
@@ -759,7 +790,7 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
 #define TR_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx->fail_cuda(e_, #call, __FILE__, __LINE__)); } while (0)
     TR_TRY(pem_alloc(ctx, &T->tile_row_ptr, (size_t)T->tile_rows + 1));
     TR_CK(cudaMemsetAsync(T->tile_row_ptr, 0, ((size_t)T->tile_rows + 1) * 4, ctx->stream));
-    TR_TRY(pem_alloc(ctx, &T->vals, (size_t)T->nnz)); TR_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)T->nnz));
+    TR_TRY(pem_alloc_bytes(ctx, (void**)&T->vals, std::max<size_t>(1, (size_t)T->nnz * pem_vsize(T->dtype)))); TR_TRY(pem_alloc(ctx, &T->rc_idx, (size_t)T->nnz));
     TR_TRY(pem_alloc(ctx, &T->tile_nnz_ptr, n + 1)); TR_TRY(pem_alloc(ctx, &T->masks, n * 16));
     TR_TRY(pem_alloc(ctx, &T->masks_t, n * 16)); TR_TRY(pem_alloc(ctx, &T->row_ptr, n * 16));
     TR_TRY(pem_alloc(ctx, &T->tile_col_idx, n)); TR_TRY(pem_alloc(ctx, &T->tile_row_idx, n));
@@ -786,10 +817,16 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
     ++ctx->launches;
     TR_CK(cudaGetLastError());
     TR_TRY(pem_scan_exclusive_i64(ctx, nptr, (int64_t)n + 1));
-    k_transpose_tiles<<<pem_div_up((int64_t)n, 128), 128, 0, ctx->stream>>>(
-        (int)n, T->tile_rows, perm, nptr, A->tile_nnz_ptr, A->masks, A->masks_t, A->tile_row_idx, A->tile_col_idx, A->col_occ,
-        A->row_occ, A->rc_idx, A->vals, T->tile_nnz_ptr, T->masks, T->masks_t, T->row_ptr, T->tile_row_idx, T->tile_col_idx,
-        T->tile_row_ptr, T->col_occ, T->row_occ, T->rc_idx, T->vals);
+    if (A->dtype == PEM_F32)
+        k_transpose_tiles<float><<<pem_div_up((int64_t)n, 128), 128, 0, ctx->stream>>>(
+            (int)n, T->tile_rows, perm, nptr, A->tile_nnz_ptr, A->masks, A->masks_t, A->tile_row_idx, A->tile_col_idx, A->col_occ,
+            A->row_occ, A->rc_idx, reinterpret_cast<const float*>(A->vals), T->tile_nnz_ptr, T->masks, T->masks_t, T->row_ptr,
+            T->tile_row_idx, T->tile_col_idx, T->tile_row_ptr, T->col_occ, T->row_occ, T->rc_idx, reinterpret_cast<float*>(T->vals));
+    else
+        k_transpose_tiles<double><<<pem_div_up((int64_t)n, 128), 128, 0, ctx->stream>>>(
+            (int)n, T->tile_rows, perm, nptr, A->tile_nnz_ptr, A->masks, A->masks_t, A->tile_row_idx, A->tile_col_idx, A->col_occ,
+            A->row_occ, A->rc_idx, A->vals, T->tile_nnz_ptr, T->masks, T->masks_t, T->row_ptr, T->tile_row_idx, T->tile_col_idx,
+            T->tile_row_ptr, T->col_occ, T->row_occ, T->rc_idx, T->vals);
     ++ctx->launches;
     TR_CK(cudaGetLastError());
     T->h_tile_row_ptr.resize((size_t)T->tile_rows + 1);

@@ -232,7 +232,7 @@ static const void* tiled_array(const pem_tiled* t, int which, size_t* bytes)
 {
     size_t n = (size_t)t->tiles;
     switch (which) {
-        case PEM_T_VALS: *bytes = (size_t)t->nnz * 8; return t->vals;
+        case PEM_T_VALS: *bytes = (size_t)t->nnz * pem_vsize(t->dtype); return t->vals;
         case PEM_T_TILE_NNZ_PTR: *bytes = (n + 1) * 4; return t->tile_nnz_ptr;
         case PEM_T_MASKS: *bytes = n * 32; return t->masks;
         case PEM_T_ROW_PTR: *bytes = n * 16; return t->row_ptr;
@@ -247,6 +247,9 @@ static const void* tiled_array(const pem_tiled* t, int which, size_t* bytes)
     *bytes = 0;
     return nullptr;
 }
+
+int pem_tiled_dtype(const pem_tiled* t) { return t ? t->dtype : -1; }
+int pem_result_dtype(const pem_result* C) { return C ? C->dtype : -1; }
 
 int pem_tiled_values_ready(pem_ctx* ctx, const pem_tiled* t)
 {
@@ -313,7 +316,7 @@ static const void* result_array(const pem_result* C, int which, size_t* bytes)
         case PEM_R_MASKS: *bytes = C->stage >= 2 ? n * 32 : 0; return C->masks;
         case PEM_R_TILE_NNZ_PTR: *bytes = C->stage >= 2 ? (n + 1) * 8 : 0; return C->tile_nnz_ptr;
         case PEM_R_ROW_COL_IDX: *bytes = C->stage >= 2 ? (size_t)C->nnz : 0; return C->row_col_idx;
-        case PEM_R_VALS: *bytes = C->stage >= 3 ? (size_t)C->nnz * 8 : 0; return C->vals;
+        case PEM_R_VALS: *bytes = C->stage >= 3 ? (size_t)C->nnz * pem_vsize(C->dtype) : 0; return C->vals;
     }
     *bytes = 0;
     return nullptr;

@@ -120,7 +120,14 @@ static inline int pem_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / 
 // ---------------------------------------------------------------------------------------
 // tiled matrix (arrays named after the reference's)
 // ---------------------------------------------------------------------------------------
+// value type of a tiled matrix / result: the reference is fp64 only (spgemm.cu:728, `ValueType`, a template
+// parameter there); fp32 is the second instantiation SURVEY.md section 8f rank 4 asks for.  The `vals`
+// pointers below are typed double* and reinterpreted as float* when dtype == PEM_F32.
+enum { PEM_F64 = 0, PEM_F32 = 1 };
+static inline size_t pem_vsize(int dtype) { return dtype == PEM_F32 ? 4 : 8; }
+
 struct pem_tiled {
+    int dtype = PEM_F64;
     int32_t rows = 0, cols = 0;
     int64_t nnz = 0;
     int32_t tile_rows = 0, tile_cols = 0, tiles = 0;
@@ -158,6 +165,7 @@ struct pem_tiled {
 // result: C or a tile-row panel of C
 // ---------------------------------------------------------------------------------------
 struct pem_result {
+    int dtype = PEM_F64;
     int32_t rb = 0, re = 0;           // panel of A' tile rows
     int32_t rows = 0, cols = 0;       // shape of the full C
     int32_t tile_cols = 0;

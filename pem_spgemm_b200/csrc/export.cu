@@ -25,11 +25,12 @@ k_export_count(int n_tile_rows, const int64_t* __restrict__ c_row_ptr, const uin
     row_cnt[(int64_t)g * 16 + r] = cnt;
 }
 
+template <class T>
 __global__ void __launch_bounds__(256)
 k_export_fill(int n_tile_rows, int rb, const int64_t* __restrict__ c_row_ptr, const int32_t* __restrict__ c_tile_col,
               const uint16_t* __restrict__ Cmasks, const int64_t* __restrict__ c_tile_nnz_ptr,
-              const double* __restrict__ C_vals, const int64_t* __restrict__ row_ptr,
-              int32_t* __restrict__ rows, int32_t* __restrict__ cols, double* __restrict__ vals)
+              const T* __restrict__ C_vals, const int64_t* __restrict__ row_ptr,
+              int32_t* __restrict__ rows, int32_t* __restrict__ cols, T* __restrict__ vals)
 {
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     int r = threadIdx.x & 15;
@@ -61,13 +62,14 @@ k_export_fill(int n_tile_rows, int rb, const int64_t* __restrict__ c_row_ptr, co
 }
 
 // deterministic two-level reduction of sum and sum|.|
+template <class T>
 __global__ void __launch_bounds__(256)
-k_checksum_partial(const double* __restrict__ v, int64_t n, double* __restrict__ part)
+k_checksum_partial(const T* __restrict__ v, int64_t n, double* __restrict__ part)
 {
     __shared__ double s1[8], s2[8];
     double a = 0, b = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        double x = v[i];
+        double x = (double)v[i];
         a += x;
         b += fabs(x);
     }
@@ -107,31 +109,39 @@ int pem_result_to_coo_device(pem_ctx* ctx, const pem_result* C, int32_t* d_rows,
     }
     PEM_TRY(pem_scan_exclusive_i64(ctx, rp, (int64_t)nrow + 1));
     if (ntr > 0 && C->tiles > 0 && (d_rows || d_cols || d_vals)) {
-        k_export_fill<<<pem_div_up((int64_t)ntr * 16, 256), 256, 0, ctx->stream>>>(
-            ntr, C->rb, C->row_ptr, C->tile_col, C->masks, C->tile_nnz_ptr, C->vals, rp, d_rows, d_cols, d_vals);
+        if (C->dtype == PEM_F32)      // d_vals then points at floats
+            k_export_fill<float><<<pem_div_up((int64_t)ntr * 16, 256), 256, 0, ctx->stream>>>(
+                ntr, C->rb, C->row_ptr, C->tile_col, C->masks, C->tile_nnz_ptr, reinterpret_cast<const float*>(C->vals), rp,
+                d_rows, d_cols, reinterpret_cast<float*>(d_vals));
+        else
+            k_export_fill<double><<<pem_div_up((int64_t)ntr * 16, 256), 256, 0, ctx->stream>>>(
+                ntr, C->rb, C->row_ptr, C->tile_col, C->masks, C->tile_nnz_ptr, C->vals, rp, d_rows, d_cols, d_vals);
         PEM_LAUNCHED();
     }
     if (!d_row_ptr) pem_free(ctx, rp);
     return PEM_OK;
 }
 
-int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, double* vals)
+static int result_to_coo_any(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, void* vals, int dtype)
 {
     PEM_RANGE("pem_result_to_coo");
     if (!ctx || !C) return PEM_ERR_ARG;
+    if (vals && C->dtype != dtype)
+        return ctx->fail(PEM_ERR_ARG, C->dtype == PEM_F32 ? "fp32 result: use pem_result_to_coo_f32" : "fp64 result: use pem_result_to_coo");
+    const size_t vsz = pem_vsize(C->dtype);
     int32_t *dr = nullptr, *dc = nullptr;
     double* dv = nullptr;
     size_t n = (size_t)C->nnz;
     int rc = PEM_OK;
     if (rows) rc = pem_alloc(ctx, &dr, n);
     if (cols && rc == PEM_OK) rc = pem_alloc(ctx, &dc, n);
-    if (vals && rc == PEM_OK) rc = pem_alloc(ctx, &dv, n);
+    if (vals && rc == PEM_OK) rc = pem_alloc_bytes(ctx, (void**)&dv, std::max<size_t>(1, n * vsz));
     if (rc == PEM_OK) rc = pem_result_to_coo_device(ctx, C, dr, dc, dv, nullptr);
     if (rc == PEM_OK && n) {
         cudaError_t e = cudaSuccess;
         if (rows && e == cudaSuccess) e = cudaMemcpyAsync(rows, dr, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (cols && e == cudaSuccess) e = cudaMemcpyAsync(cols, dc, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (vals && e == cudaSuccess) e = cudaMemcpyAsync(vals, dv, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (vals && e == cudaSuccess) e = cudaMemcpyAsync(vals, dv, n * vsz, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = ctx->fail_cuda(e, "D2H copy of the COO result", __FILE__, __LINE__);
     }
@@ -139,10 +149,21 @@ int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t*
     return rc;
 }
 
+int pem_result_to_coo(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, double* vals)
+{
+    return result_to_coo_any(ctx, C, rows, cols, vals, PEM_F64);
+}
+
+int pem_result_to_coo_f32(pem_ctx* ctx, const pem_result* C, int32_t* rows, int32_t* cols, float* vals)
+{
+    return result_to_coo_any(ctx, C, rows, cols, vals, PEM_F32);
+}
+
 int pem_result_to_csr(pem_ctx* ctx, const pem_result* C, int64_t* row_ptr, int32_t* cols, double* vals)
 {
     PEM_RANGE("pem_result_to_csr");
     if (!ctx || !C) return PEM_ERR_ARG;
+    if (vals && C->dtype != PEM_F64) return ctx->fail(PEM_ERR_ARG, "pem_result_to_csr returns fp64 values: use pem_result_to_coo_f32 for an fp32 result");
     const int64_t first_row = (int64_t)C->rb * 16;
     const int64_t nrows = std::max<int64_t>(0, std::min<int64_t>(C->rows, (int64_t)C->re * 16) - first_row);
     int32_t* dc = nullptr;
@@ -175,7 +196,8 @@ int pem_result_checksum(pem_ctx* ctx, const pem_result* C, double* sum, double* 
     const int nb = 1024;
     double* part = nullptr;
     PEM_TRY(pem_alloc(ctx, &part, (size_t)2 * nb));
-    k_checksum_partial<<<nb, 256, 0, ctx->stream>>>(C->vals, C->nnz, part);
+    if (C->dtype == PEM_F32) k_checksum_partial<float><<<nb, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(C->vals), C->nnz, part);
+    else k_checksum_partial<double><<<nb, 256, 0, ctx->stream>>>(C->vals, C->nnz, part);
     PEM_LAUNCHED();
     std::vector<double> h((size_t)2 * nb);
     PEM_CK(cudaMemcpyAsync(h.data(), part, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -506,9 +506,11 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     *out = nullptr;
     if (!ctx || !A || !B) return PEM_ERR_ARG;
     if (A->cols != B->rows) return ctx->fail(PEM_ERR_ARG, "inner dimensions differ (A.cols != B.rows)");
+    if (A->dtype != B->dtype) return ctx->fail(PEM_ERR_ARG, "operands have different value types");
     if (rb < 0 || re < rb || re > A->tile_rows) return ctx->fail(PEM_ERR_ARG, "tile-row panel out of range");
     PEM_CK(cudaSetDevice(ctx->device));
     pem_result* C = new pem_result();
+    C->dtype = A->dtype;
     C->rb = rb; C->re = re; C->rows = A->rows; C->cols = B->cols; C->tile_cols = B->tile_cols;
     const int nrows = re - rb;
     ctx->last_sort_passes = -1;

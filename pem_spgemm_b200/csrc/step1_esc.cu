@@ -316,11 +316,11 @@ k_compact(const int32_t* __restrict__ split, const int64_t* __restrict__ chunk_o
 // off[r] = first pair of row r (lower bound of r among the keys' row fields), off[nrows] = F.
 template <class KeyT>
 __global__ void __launch_bounds__(256)
-k_row_offsets(int nrows, int npairs, int wbits, const KeyT* __restrict__ keys, int* __restrict__ off)
+k_row_offsets(int nrows, const int64_t* __restrict__ d_npairs, int wbits, const KeyT* __restrict__ keys, int* __restrict__ off)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > nrows) return;
-    int lo = 0, hi = npairs;
+    int lo = 0, hi = (int)*d_npairs;           // the kept-pair count is still on its way to the host
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if ((int64_t)(keys[mid] >> wbits) < (int64_t)r) lo = mid + 1; else hi = mid;
@@ -489,47 +489,67 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     }
     E_CK(cudaMemsetAsync(chunk_off + nchunks, 0, 8, ctx->stream));
     E_TRY(pem_scan_exclusive_i64(ctx, chunk_off, (int64_t)nchunks + 1));
-    E_CK(cudaMemcpyAsync(ctx->h_scalars, chunk_off + nchunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    E_CK(cudaStreamSynchronize(ctx->stream));
-    F = ctx->h_scalars[0];
-    tr.mark("expand done, F known");
-    C->pairs = F;
-    if (F == 0) {
-        cleanup();
-        return PEM_OK;
-    }
-    E_TRY(pem_alloc(ctx, &key_a, (size_t)F));
-    E_TRY(pem_alloc(ctx, &val_a, (size_t)F));
+    const int64_t* d_F = chunk_off + nchunks;              // kept pairs, on the device
+    // Short rows (banded / stencil matrices) are sorted row by row in shared memory: one pass over the
+    // pairs.  Power-law inputs have rows of millions of pairs and keep the global radix sort.  Whether every
+    // row is short is decided from the longest row, which travels to the host together with F: one stall.
+    const bool consider_rows = P < 0x7fffffffLL && wbits + RS_SMALL_BITS <= 32 && !(ctx->opt_esc_variant & 2);
     if (staged) {
+        // compaction target and sort buffer sized by the products (F <= P is not known on the host yet)
+        E_TRY(pem_alloc(ctx, &key_a, (size_t)P));
+        E_TRY(pem_alloc(ctx, &val_a, (size_t)P));
         k_compact<KeyT><<<nchunks, 256, 0, ctx->stream>>>(split, chunk_off, key_b, val_b, key_a, val_a);
         E_LAUNCHED();
-        pem_free(ctx, key_b);
-        pem_free(ctx, val_b);
+        E_CK(cudaMemsetAsync(ctx->d_scalars + SC_MAXD, 0, 8, ctx->stream));
+        if (consider_rows) {
+            E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
+            k_row_offsets<KeyT><<<pem_div_up((int64_t)nrows + 1, 256), 256, 0, ctx->stream>>>(nrows, d_F, wbits, key_a, seg_off);
+            E_LAUNCHED();
+            k_max_segment<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, seg_off, ctx->d_scalars);
+            E_LAUNCHED();
+        }
+        E_CK(cudaMemcpyAsync(ctx->h_scalars, d_F, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        E_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        E_CK(cudaStreamSynchronize(ctx->stream));
+        F = ctx->h_scalars[0];
+        tr.mark("expand + compact done, F and the longest row known");
+        C->pairs = F;
+        if (F == 0) {
+            cleanup();
+            return PEM_OK;
+        }
     } else {
+        E_CK(cudaMemcpyAsync(ctx->h_scalars, d_F, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        E_CK(cudaStreamSynchronize(ctx->stream));
+        F = ctx->h_scalars[0];
+        tr.mark("count pass done, F known");
+        C->pairs = F;
+        if (F == 0) {
+            cleanup();
+            return PEM_OK;
+        }
+        E_TRY(pem_alloc(ctx, &key_a, (size_t)F));
+        E_TRY(pem_alloc(ctx, &val_a, (size_t)F));
         k_expand<KeyT, 1, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
             np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
             B->row_occ, jmin, wbits, ctx->opt_keep_empty, chunk_off, nullptr, key_a, val_a);
         E_LAUNCHED();
-    }
-    E_TRY(pem_alloc(ctx, &key_b, (size_t)F));
-    E_TRY(pem_alloc(ctx, &val_b, (size_t)F));
-    // Short rows (banded / stencil matrices) are sorted row by row in shared memory: one pass over the
-    // pairs.  Power-law inputs have rows of millions of pairs and keep the global radix sort.
-    int by_rows = 0;                        // 1: every row holds <= 1024 pairs
-    if (F < 0x7fffffffLL && wbits + RS_SMALL_BITS <= 32 && !(ctx->opt_esc_variant & 2)) {
-        E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
+        E_TRY(pem_alloc(ctx, &key_b, (size_t)F));
+        E_TRY(pem_alloc(ctx, &val_b, (size_t)F));
         E_CK(cudaMemsetAsync(ctx->d_scalars + SC_MAXD, 0, 8, ctx->stream));
-        k_row_offsets<KeyT><<<pem_div_up((int64_t)nrows + 1, 256), 256, 0, ctx->stream>>>(nrows, (int)F, wbits, key_a, seg_off);
-        E_LAUNCHED();
-        k_max_segment<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, seg_off, ctx->d_scalars);
-        E_LAUNCHED();
-        E_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (consider_rows) {
+            E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
+            k_row_offsets<KeyT><<<pem_div_up((int64_t)nrows + 1, 256), 256, 0, ctx->stream>>>(nrows, d_F, wbits, key_a, seg_off);
+            E_LAUNCHED();
+            k_max_segment<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, seg_off, ctx->d_scalars);
+            E_LAUNCHED();
+        }
+        E_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
         E_CK(cudaStreamSynchronize(ctx->stream));
-        const int64_t longest = ctx->h_scalars[0];
-        // (a 1024-thread block sorting up to 32768 pairs of a row was tried for config 3's ~13 K-pair rows:
-        //  4.5 ms against 2.7 ms for the radix sort)
-        if (longest <= RS_SMALL) by_rows = 1;
     }
+    // (a 1024-thread block sorting up to 32768 pairs of a row was tried for config 3's ~13 K-pair rows:
+    //  4.5 ms against 2.7 ms for the radix sort)
+    const int by_rows = consider_rows && ctx->h_scalars[1] <= RS_SMALL ? 1 : 0;       // 1: every row holds <= 1024 pairs
     ctx->last_sort_passes = by_rows ? 0 : (wbits + rbits + 7) / 8;
     if (by_rows) {
         KT_BEGIN(KT_SORT);

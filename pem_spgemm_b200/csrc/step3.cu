@@ -21,6 +21,7 @@
 //                them by ANDing two words of the bit-transposed hit blocks step 2 left behind.
 // Measured on B200 (config 4: 12.1 ms against 12.7 ms; config 2: 5.1 ms against 1.3 ms, hub tiles serialise
 // on single warps), so it stays an option.  Also selectable: the row-owner kernel (sixteen lanes per tile).
+#include <algorithm>
 #include <climits>
 
 #include "engine.cuh"
@@ -29,8 +30,9 @@ namespace {
 
 // all products of one (A tile row record, B tile column record) combination, ascending k
 // (ao, bo = index of the tiles' first values; value indices stay 32-bit: one IMAD.WIDE per load)
-__device__ __forceinline__ double pair_products(unsigned ar, unsigned bc, unsigned ao, unsigned bo,
-                                                const double* __restrict__ A_vals, const double* __restrict__ B_vals_t, double acc)
+template <class T>
+__device__ __forceinline__ T pair_products(unsigned ar, unsigned bc, unsigned ao, unsigned bo,
+                                           const T* __restrict__ A_vals, const T* __restrict__ B_vals_t, T acc)
 {
     unsigned m = ar & bc & 0xFFFFu;
     if (m) {
@@ -48,14 +50,15 @@ __device__ __forceinline__ double pair_products(unsigned ar, unsigned bc, unsign
 
 // one C nonzero (r, c) of a tile with pairs [ps, pe): the candidate pairs come from the hit blocks
 // (word 16+r of 32-pair block b has bit i set iff pair 32b+i touches C row r; word c likewise for columns)
-__device__ __forceinline__ double entry_by_hits(unsigned r, unsigned c, int64_t ps, int64_t pe,
-                                                const int2* __restrict__ pairs, const uint32_t* __restrict__ hit_t,
-                                                const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
-                                                const uint32_t* __restrict__ A_row_rec,
-                                                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals_t,
-                                                const uint32_t* __restrict__ B_col_rec)
+template <class T>
+__device__ __forceinline__ T entry_by_hits(unsigned r, unsigned c, int64_t ps, int64_t pe,
+                                           const int2* __restrict__ pairs, const uint32_t* __restrict__ hit_t,
+                                           const uint32_t* __restrict__ A_off, const T* __restrict__ A_vals,
+                                           const uint32_t* __restrict__ A_row_rec,
+                                           const uint32_t* __restrict__ B_off, const T* __restrict__ B_vals_t,
+                                           const uint32_t* __restrict__ B_col_rec)
 {
-    double acc = 0.0;
+    T acc = 0;
     for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
         unsigned w = hit_t[base + 16 + r] & hit_t[base + c];
         if (base < ps) w &= 0xFFFFFFFFu << (unsigned)(ps - base);
@@ -118,13 +121,13 @@ k_step3_classes(int64_t n_tiles, int small_e, int small_np,
             const unsigned ao = A_off[ab.x], bo = B_off[ab.y];
             for (int e = 0; e < E; ++e) {
                 const unsigned rcb = rcs[e];
-                out[e] = pair_products(arec[rcb >> 4], brec[rcb & 15u], ao, bo, A_vals, B_vals_t, 0.0);
+                out[e] = pair_products<double>(arec[rcb >> 4], brec[rcb & 15u], ao, bo, A_vals, B_vals_t, 0.0);
             }
         } else {
             for (int e = 0; e < E; ++e) {
                 const unsigned rcb = rcs[e];
-                out[e] = entry_by_hits(rcb >> 4, rcb & 15u, ps, pe, pairs, hit_t,
-                                       A_off, A_vals, A_row_rec, B_off, B_vals_t, B_col_rec);
+                out[e] = entry_by_hits<double>(rcb >> 4, rcb & 15u, ps, pe, pairs, hit_t,
+                                               A_off, A_vals, A_row_rec, B_off, B_vals_t, B_col_rec);
             }
         }
     }
@@ -185,8 +188,8 @@ k_step3_classes(int64_t n_tiles, int small_e, int small_np,
                 const int e = e0 + lane;
                 if (e < Et) {
                     const unsigned rcb = rcs[e];
-                    out[e] = entry_by_hits(rcb >> 4, rcb & 15u, pst, pst + npt, pairs, hit_t,
-                                           A_off, A_vals, A_row_rec, B_off, B_vals_t, B_col_rec);
+                    out[e] = entry_by_hits<double>(rcb >> 4, rcb & 15u, pst, pst + npt, pairs, hit_t,
+                                                   A_off, A_vals, A_row_rec, B_off, B_vals_t, B_col_rec);
                 }
             }
         }
@@ -214,18 +217,19 @@ k_block_tiles(int64_t n_tiles, const int64_t* __restrict__ c_tile_nnz_ptr, int32
     }
 }
 
-template <bool RC>
+template <class T>          // value type: double (the reference's ValueType, spgemm.cu:728) or float
 __global__ void __launch_bounds__(S3E_ENTRIES, 16)
 k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
                 const int64_t* __restrict__ c_tile_nnz_ptr, const uint8_t* __restrict__ c_row_col_idx,
                 const uint32_t* __restrict__ Cmasks32,
                 const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
                 const uint32_t* __restrict__ hit_t,
-                const uint32_t* __restrict__ A_off, const double* __restrict__ A_vals,
+                const uint32_t* __restrict__ A_off, const T* __restrict__ A_vals,
                 const uint32_t* __restrict__ A_row_rec,
-                const uint32_t* __restrict__ B_off, const double* __restrict__ B_vals_t,
-                const uint32_t* __restrict__ B_col_rec, double* __restrict__ C_vals)
+                const uint32_t* __restrict__ B_off, const T* __restrict__ B_vals_t,
+                const uint32_t* __restrict__ B_col_rec, T* __restrict__ C_vals)
 {
+    constexpr bool RC = false;      // (r, c) from the tile mask; reading Ctiles_rowColIdx instead is 8 % faster here but producing it costs more
     __shared__ int s_off[S3E_TMAX];
     const int tid = threadIdx.x;
     const int64_t n0 = (int64_t)blockIdx.x * S3E_ENTRIES;
@@ -292,8 +296,8 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
         r = 2u * wi + (b >> 4);
         c = b & 15u;
     }
-    C_vals[n] = entry_by_hits(r, c, pair_ptr[t], pair_ptr[t + 1], pairs, hit_t,
-                              A_off, A_vals, A_row_rec, B_off, B_vals_t, B_col_rec);
+    C_vals[n] = entry_by_hits<T>(r, c, pair_ptr[t], pair_ptr[t + 1], pairs, hit_t,
+                                 A_off, A_vals, A_row_rec, B_off, B_vals_t, B_col_rec);
 }
 
 // =========================================================================================
@@ -400,7 +404,9 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_tiled_wait_vals(ctx, A));        // freshly converted operands: the values may still be on their way
     PEM_TRY(pem_tiled_wait_vals(ctx, B));
-    PEM_TRY(pem_alloc(ctx, &C->vals, (size_t)C->nnz));
+    if (C->dtype == PEM_F32 && (!C->pair_hit || !C->s3_entries))
+        return ctx->fail(PEM_ERR_ARG, "fp32 products run the default kernels only (PEM_OPT_OWNER 0 / 2)");
+    PEM_TRY(pem_alloc_bytes(ctx, (void**)&C->vals, std::max<size_t>(1, (size_t)C->nnz * pem_vsize(C->dtype))));
     const bool by_records = C->pair_hit != nullptr;         // step 2 ran the pair kernel
     // the class kernel reads every nonzero's (r, c) from Ctiles_rowColIdx; the entry-owner kernel derives it
     // from the tile mask (measured on config 4: 11.6 ms against 12.7 ms with the bytes, but producing them costs 1.0 ms)
@@ -422,7 +428,13 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
 #define S3E_ARGS C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, C->row_col_idx, reinterpret_cast<const uint32_t*>(C->masks), \
             C->pair_ptr, C->pair_list, C->pair_hit, A->tile_nnz_ptr, A->vals, A->row_rec, B->tile_nnz_ptr, B->vals_t, B->col_rec, C->vals
-        k_step3_entries<false><<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(S3E_ARGS);
+        if (C->dtype == PEM_F32)
+            k_step3_entries<float><<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(
+                C->nnz, C->tiles, C->blk_tile, C->tile_nnz_ptr, C->row_col_idx, reinterpret_cast<const uint32_t*>(C->masks),
+                C->pair_ptr, C->pair_list, C->pair_hit, A->tile_nnz_ptr, reinterpret_cast<const float*>(A->vals), A->row_rec,
+                B->tile_nnz_ptr, reinterpret_cast<const float*>(B->vals_t), B->col_rec, reinterpret_cast<float*>(C->vals));
+        else
+            k_step3_entries<double><<<(unsigned)nblk, S3E_ENTRIES, 0, ctx->stream>>>(S3E_ARGS);
 #undef S3E_ARGS
         PEM_LAUNCHED();
     } else if (C->nnz > 0 && by_records) {

@@ -118,6 +118,53 @@ def test_csr_in_and_csr_out(engine, shape, nnz, seed, where):
     C.free(); T.free(); A.free()
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_fp32_instantiation_matches_fp32_oracle(engine, k):
+    """the second value type.  fp32 operands, single-precision fma in the same
+    ascending-k order: structure identical to the fp64 product, value bits equal to the fp32 oracle's."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    V32 = V.astype(np.float32)
+    A = engine.convert_coo(rows, cols, I, J, V32, dtype=np.float32)
+    assert A.dtype == np.float32
+    O = tiles.tile_format(rows, cols, I, J, V32.astype(np.float64))
+    assert np.array_equal(A.array("vals"), O.vals.astype(np.float32))
+    assert np.array_equal(A.array("masks").reshape(-1, 16), O.masks)
+    B = engine.transpose(A) if tb else A
+    oA = host.coo_to_csr(rows, cols, I, J, V32.astype(np.float64))
+    oB = host.transpose(oA) if tb else oA
+    oC = host.spgemm_f32(oA, oB)
+    bounds = engine.partition_panels(A, B, 2)
+    parts = []
+    for p in range(2):
+        C = engine.spgemm(A, B, panel=(bounds[p], bounds[p + 1]))
+        assert C.dtype == np.float32
+        parts.append(C.to_coo())
+        if p == 0:
+            s, a = C.checksum()
+            np.testing.assert_allclose([s, a], [parts[0][2].astype(np.float64).sum(), np.abs(parts[0][2].astype(np.float64)).sum()],
+                                       rtol=1e-9, atol=1e-9)
+        C.free()
+    r = np.concatenate([x[0] for x in parts]); c = np.concatenate([x[1] for x in parts]); v = np.concatenate([x[2] for x in parts])
+    ro, co, vo = oC.to_coo()
+    assert v.dtype == np.float32 and np.array_equal(r, ro) and np.array_equal(c, co)
+    np.testing.assert_allclose(v, vo, rtol=1e-5, atol=0)             # stated fp32 tolerance
+    assert np.array_equal(v, vo)                                     # same fma order => same bits
+    # mixing value types and the fp64-only kernels are refused, not silently converted
+    A64 = engine.convert_coo(rows, cols, I, J, V)
+    with pytest.raises(pem.PemError):
+        engine.spgemm(A64 if not tb else A, A if not tb else engine.transpose(A64))
+    engine.set_option(pem.OPT_OWNER, 3)
+    try:
+        with pytest.raises(pem.PemError):
+            engine.spgemm(A, B)
+    finally:
+        engine.set_option(pem.OPT_OWNER, 0)
+    A64.free()
+    if B is not A:
+        B.free()
+    A.free()
+
+
 def test_conversion_dense_tile_and_empty(engine):
     I, J = np.divmod(np.arange(256, dtype=np.int32), 16)
     V = np.arange(256, dtype=np.float64)

@@ -123,3 +123,14 @@ def test_tile_format_layout_small():
         assert np.array_equal(m, T.masks[tt]) and np.array_equal(mt, T.masks_t[tt])
         cnt = np.array([bin(int(x)).count("1") for x in m])
         assert np.array_equal(T.row_ptr[tt], (np.cumsum(cnt) - cnt).astype(np.uint8))
+
+
+def test_fp32_oracle_agrees_with_fp64_on_exactly_representable_products():
+    """Integer-valued inputs: every partial sum is exact in both precisions, so the fp32 instantiation of the
+    numeric pass must reproduce the fp64 one after rounding; structure is shared."""
+    rows, cols, I, J, V = synth.random_sparse(300, 300, 4000, seed=12, integer_values=True)
+    A = host.coo_to_csr(rows, cols, I, J, V)
+    C64, C32 = host.spgemm(A, A), host.spgemm_f32(A, A)
+    assert C32.val.dtype == np.float32
+    assert np.array_equal(C64.ptr, C32.ptr) and np.array_equal(C64.idx, C32.idx)
+    assert np.array_equal(C64.val.astype(np.float32), C32.val)

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round-2 evidence run (on the GPU box): launch lists of every config and `ncu --set full` of the hot kernels of
+# the second SpGEMM iteration, exported to text on the box (the .ncu-rep files are too large to travel back).
+cd "$(dirname "$0")/.."
+tag=${1:-r2p}
+RX='k_step3_entries|k_step2_pairs|k_expand|Onesweep|k_row_sort|k_step1_count|k_step1_fill|k_build_tiles|k_ctiles'
+full() {   # config, launch-skip, count, extra quick_bench flags
+  local k=$1 skip=$2 cnt=$3; shift 3
+  timeout 1200 ncu --set full --clock-control none -k regex:"$RX" --launch-skip $skip -c $cnt -f -o gpurun_out/full_${tag}_c$k \
+      python tools/quick_bench.py $k "$@" > gpurun_out/ncufull_${tag}_c$k.log 2>&1
+  python tools/ncu_summary.py gpurun_out/full_${tag}_c$k.ncu-rep > gpurun_out/ncu_${tag}_c$k.txt 2>&1
+  ncu -i gpurun_out/full_${tag}_c$k.ncu-rep --page raw --csv > gpurun_out/ncuraw_${tag}_c$k.csv 2>/dev/null
+  rm -f gpurun_out/full_${tag}_c$k.ncu-rep
+  tail -n 2 gpurun_out/ncufull_${tag}_c$k.log
+}
+for k in 1 2 3 4; do bash tools/launch_list.sh $tag $k; done
+QB_FLAGS="--panels 16 --reps 1" bash tools/launch_list.sh $tag 5
+full 1 5 4 --reps 2          # bitmap step 1: build_tiles once, then count, fill, pairs, entries
+full 2 9 8 --reps 2          # radix path: build_tiles, then expand, 4 x onesweep, ctiles, pairs, entries
+full 3 9 8 --reps 2
+full 4 6 5 --reps 2          # row sort: build_tiles, then expand, row_sort, ctiles, pairs, entries
+full 5 9 8 --panels 16 --reps 1     # second panel of the first product
+du -sh gpurun_out

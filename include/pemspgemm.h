@@ -59,11 +59,16 @@ typedef enum pem_option {
      * SPA and NSPARSE hashing `B_tileCols > 512*32` (spgemm.cu:1142). */
     PEM_OPT_STEP1_PATH = 2,
     /* thread mapping of step 3 (and of step 2 for value 1).  Results are bit-identical.
-     * 0 (default) / 2 = entry-owner: one thread per C nonzero over the flat nonzero index space
+     * 0 (default) = automatic: the window kernel (4) when C holds at least four nonzeros per tile pair (stencil /
+     *     FEM products), else the entry-owner kernel (2)
+     * 2 = entry-owner: one thread per C nonzero over the flat nonzero index space
      * 1 = row-owner: sixteen lanes per C' tile, lane = tile row (steps 2 and 3; no pair kernel)
      * 3 = tile-class kernel: a warp takes 32 consecutive C' tiles; small tiles get one thread each, the
      *     others one warp each with their pairs' records staged in shared memory (or, for long pair
-     *     lists, found through step 2's hit blocks) */
+     *     lists, found through step 2's hit blocks)
+     * 4 = window kernel: a block takes the C' tiles of a 128-pair window of the pair list, stages the pairs' A row
+     *     records / B column records in shared memory (128-bit asynchronous copies), decodes the window's nonzeros
+     *     cooperatively and lets each thread own nonzeros */
     PEM_OPT_OWNER = 3,
     /* tuning of the tile-class kernel: a C' tile with at most SMALL_NNZ nonzeros (default 8) and at most
      * SMALL_PAIRS pairs (default 64) is handled by one thread, any other tile by one warp */
@@ -158,7 +163,7 @@ int pem_convert_coo(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
  * ship as double only): same conversion with float values.  A product of two fp32 operands accumulates with
  * single-precision fma in the same ascending-k order and yields an fp32 result (pem_result_to_coo_f32;
  * pem_result_get(PEM_R_VALS) and pem_tiled_get(PEM_T_VALS) then move 4-byte values).  Operands of different
- * value types cannot be multiplied.  fp32 runs the default kernels (PEM_OPT_OWNER 0 / 2). */
+ * value types cannot be multiplied.  fp32 runs the default kernels (PEM_OPT_OWNER 0 / 2 / 4). */
 int pem_convert_coo_f32(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz,
                         const int32_t* I, const int32_t* J, const float* V, int transpose,
                         pem_tiled** out, pem_times* times);

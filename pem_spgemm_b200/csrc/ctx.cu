@@ -152,7 +152,7 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
             ctx->opt_step1_path = (int)value;
             return PEM_OK;
         case PEM_OPT_OWNER:
-            if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0..3");
+            if (value < 0 || value > 4) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_OWNER must be 0..4");
             ctx->opt_owner = (int)value;
             return PEM_OK;
         case PEM_OPT_TRACE: ctx->opt_trace = (int)value; return PEM_OK;

@@ -33,7 +33,7 @@ struct pem_ctx {
     int last_sort_passes = -1;   // step 1 of the last product: -1 = no sort (bitmap path), 0 = block-local row sort, n = n radix passes
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH
-    int opt_owner = 0;           // PEM_OPT_OWNER: 0 / 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel
+    int opt_owner = 0;           // PEM_OPT_OWNER: 0 = automatic (window or entry-owner), 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel, 4 = window kernel
     int opt_trace = 0;           // PEM_OPT_TRACE: host-side timeline of step 1 on stderr
     int opt_esc_variant = 0;     // PEM_OPT_ESC_VARIANT: bit 0 = count-then-write expansion, bit 1 = no block-local row sort
     int opt_step2_kernel = 0;    // PEM_OPT_STEP2_KERNEL: 0 / 1 = lane per pair, 2 = sixteen lanes per C' tile

@@ -363,7 +363,7 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     PEM_TRY(pem_alloc(ctx, &C->tile_nnz_ptr, (size_t)C->tiles + 1));
     const bool rows_variant = ctx->opt_owner == 1;
     if (C->dtype == PEM_F32 && (rows_variant || ctx->opt_owner == 3))
-        return ctx->fail(PEM_ERR_ARG, "fp32 products run the default kernels only (PEM_OPT_OWNER 0 / 2)");
+        return ctx->fail(PEM_ERR_ARG, "fp32 products run the default kernels only (PEM_OPT_OWNER 0 / 2 / 4)");
     if (rows_variant) {
         if (C->tiles > 0) {
             k_step2_masks<<<pem_div_up(C->tiles * 16, 256), 256, 0, ctx->stream>>>(

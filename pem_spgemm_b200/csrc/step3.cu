@@ -301,6 +301,193 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
 }
 
 // =========================================================================================
+// PEM_OPT_OWNER = 4: WINDOW kernel.  A block takes one window of the pair list: the C' tiles whose first
+// pair lies in [w * NP, (w + 1) * NP) (at most NP tiles, found through k_window_tiles' table).  The block
+//   1. stages, for every pair of the window, A's sixteen row records and B's sixteen column records
+//      (128 bytes per pair, eight lanes per pair, 128-bit asynchronous copies) and the two value offsets in
+//      shared memory, next to the tiles' masks, pair ranges and nonzero offsets;
+//   2. decodes the window's nonzeros cooperatively while those copies are in flight: one lane per 32-bit
+//      mask word (two tile rows), the word's rank by an 8-lane scan, one 16-bit code
+//      (tile << 8 | r << 4 | c) per nonzero;
+//   3. lets every thread own nonzeros (consecutive threads = consecutive nonzeros, so C is written
+//      coalesced): the pair loop and both record reads run out of shared memory, only the two value
+//      gathers per product touch global memory.
+// No per-thread tile search, no rank select, no hit words; the dependent chain of the entry-owner kernel
+// (tile offset -> mask -> hit words -> pair -> records -> values, paid per nonzero with a global-memory
+// latency each) becomes window -> pairs -> records, taken once per window with all loads of a stage in
+// flight together, then values.  The window's last tile may own more pairs than are staged (hub tiles of
+// power-law inputs): it is computed through the hit blocks like the entry-owner kernel does.
+// Measured and rejected (profiles/r02_step3_windows.md): the tiles' VALUES staged in shared memory as well
+// (8-byte cp.async, packed per warp: the ~65 instructions per pair of the copy loop cost more than the
+// load stalls they remove, 19.1 ms against 11.2 ms on config 4) and 1-D bulk copies (cp.async.bulk) for the
+// per-pair payloads (a warp issues them one lane at a time, ~36 ns per copy, tools/ubench/bulk_rate.cu).
+// =========================================================================================
+constexpr int S3W_THREADS = 256;
+constexpr int S3W_ECAP = 2048;      // nonzeros decoded per pass
+
+// win_tile[w] = first tile whose pair list starts at or after pair w * np (w = 0 .. n_windows)
+__global__ void __launch_bounds__(256)
+k_window_tiles(int64_t n_tiles, int64_t n_windows, int np, const int64_t* __restrict__ pair_ptr, int32_t* __restrict__ win_tile)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const int64_t lo = t == 0 ? 0 : pair_ptr[t - 1] / np + 1;
+    const int64_t hi = min(pair_ptr[t] / np, n_windows);
+    for (int64_t w = lo; w <= hi; ++w) win_tile[w] = (int32_t)t;
+    if (t == n_tiles) win_tile[n_windows] = (int32_t)n_tiles;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// shared-memory layout of the window kernel
+template <int NP, int SCAP>
+struct S3WLayout {
+    static constexpr int REC = 0;
+    static constexpr int VOFF = REC + SCAP * 128;
+    static constexpr int MASK = VOFF + SCAP * 8;
+    static constexpr int PP = MASK + NP * 32;
+    static constexpr int NZ = PP + (NP + 4) * 4;
+    static constexpr int CODE = NZ + (NP + 4) * 4;
+    static constexpr int BYTES = CODE + S3W_ECAP * 2;
+};
+
+template <class T, int NP, int SCAP, int MINB>   // window pairs, staged pairs (multiple of 32)
+__global__ void __launch_bounds__(S3W_THREADS, MINB)
+k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict__ c_tile_nnz_ptr,
+                const uint4* __restrict__ Cmasks128, const int64_t* __restrict__ pair_ptr,
+                const int2* __restrict__ pairs, const uint32_t* __restrict__ hit_t,
+                const uint32_t* __restrict__ A_off, const T* __restrict__ A_vals, const uint4* __restrict__ A_row_rec4,
+                const uint32_t* __restrict__ B_off, const T* __restrict__ B_vals_t, const uint4* __restrict__ B_col_rec4,
+                T* __restrict__ C_vals)
+{
+    static_assert(SCAP % 32 == 0 && SCAP >= NP && SCAP / 32 <= S3W_THREADS / 32 && NP <= 128, "window shape");
+    using L = S3WLayout<NP, SCAP>;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_raw + L::REC);     // pair j: A row records [32j .. 32j+15], B column records [32j+16 .. 32j+31]
+    uint2* s_voff = reinterpret_cast<uint2*>(s_raw + L::VOFF);         // pair j: first value of the A tile, of the B tile
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_raw + L::MASK);
+    int* s_pp = reinterpret_cast<int*>(s_raw + L::PP);                 // pair ranges, relative to the window's first pair
+    int* s_nz = reinterpret_cast<int*>(s_raw + L::NZ);                 // nonzero offsets, relative to the window's first nonzero
+    uint16_t* s_code = reinterpret_cast<uint16_t*>(s_raw + L::CODE);
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ta = win_tile[blockIdx.x], tb = win_tile[blockIdx.x + 1];
+    const int nt = (int)(tb - ta);
+    if (nt <= 0) return;                                        // a hub tile spans this whole window
+    const int64_t P0 = pair_ptr[ta], N0 = c_tile_nnz_ptr[ta];
+    const int64_t p_last = pair_ptr[tb] - P0, p_prev = pair_ptr[tb - 1] - P0;
+    const int ns = p_last <= SCAP ? (int)p_last : (int)p_prev;  // staged pairs (p_prev < NP)
+    // ---- 1. asynchronous copies: records of the window's pairs; their value offsets ---------------------
+    if (warp * 32 < ns) {
+        const int j0 = warp * 32, jm = j0 + lane;
+        int2 ab = make_int2(0, 0);
+        if (jm < ns) ab = pairs[P0 + jm];
+        const int part = lane & 7;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                           // four pairs per warp-wide 128-bit copy
+            const int jl = q * 4 + (lane >> 3);
+            const unsigned ax = (unsigned)__shfl_sync(FULL, ab.x, jl), by = (unsigned)__shfl_sync(FULL, ab.y, jl);
+            if (j0 + jl < ns)
+                cp_async16(reinterpret_cast<uint4*>(s_rec) + (j0 + jl) * 8 + part,
+                           part < 4 ? A_row_rec4 + (size_t)ax * 4 + part : B_col_rec4 + (size_t)by * 4 + (part - 4));
+        }
+        if (jm < ns) s_voff[jm] = make_uint2(A_off[ab.x], B_off[ab.y]);
+    }
+    for (int x = tid; x <= nt; x += S3W_THREADS) {
+        s_pp[x] = (int)min(pair_ptr[ta + x] - P0, (int64_t)0x3fffffff);
+        s_nz[x] = (int)(c_tile_nnz_ptr[ta + x] - N0);
+    }
+    for (int x = tid; x < nt * 2; x += S3W_THREADS) reinterpret_cast<uint4*>(s_mask)[x] = Cmasks128[ta * 2 + x];
+    __syncthreads();
+    const int ne = s_nz[nt];
+    for (int e0 = 0; e0 < ne; e0 += S3W_ECAP) {
+        // ---- 2. decode: lane = one mask word (rows 2w, 2w+1) of one tile ---------------------------------
+        for (int it0 = warp * 32; it0 < nt * 8; it0 += S3W_THREADS) {
+            const int it = it0 + lane;
+            unsigned word = it < nt * 8 ? s_mask[it] : 0u;
+            const int pc = __popc(word);
+            int incl = pc;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o, 8);
+                if ((lane & 7) >= o) incl += v;
+            }
+            if (word) {
+                int rank = s_nz[it >> 3] + (incl - pc) - e0;
+                const unsigned base = (unsigned)(it >> 3) << 8 | (unsigned)(it & 7) << 5;
+                do {
+                    const unsigned b = __ffs(word) - 1;
+                    word &= word - 1;
+                    if ((unsigned)rank < (unsigned)S3W_ECAP) s_code[rank] = (uint16_t)(base + b);
+                    ++rank;
+                } while (word);
+            }
+        }
+        if (e0 == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        // ---- 3. one thread per nonzero ------------------------------------------------------------------
+        const int e1 = min(ne, e0 + S3W_ECAP);
+        for (int i = e0 + tid; i < e1; i += S3W_THREADS) {
+            const unsigned code = s_code[i - e0];
+            const unsigned tl = code >> 8, r = (code >> 4) & 15u, c = code & 15u;
+            const int js = s_pp[tl], je = s_pp[tl + 1];
+            T acc = 0;
+            if (je <= ns) {
+                const uint32_t* ra = s_rec + js * 32 + r;
+                const uint32_t* rb = s_rec + js * 32 + 16 + c;
+                const uint2* vo = s_voff + js;
+                for (int j = js; j < je; ++j, ra += 32, rb += 32, ++vo) {
+                    const unsigned ar = *ra, bc = *rb;
+                    if (ar & bc & 0xFFFFu) {
+                        const uint2 o = *vo;
+                        acc = pair_products<T>(ar, bc, o.x, o.y, A_vals, B_vals_t, acc);
+                    }
+                }
+            } else {
+                acc = entry_by_hits<T>(r, c, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
+                                       A_off, A_vals, reinterpret_cast<const uint32_t*>(A_row_rec4),
+                                       B_off, B_vals_t, reinterpret_cast<const uint32_t*>(B_col_rec4));
+            }
+            C_vals[N0 + i] = acc;
+        }
+        if (e0 + S3W_ECAP < ne) __syncthreads();
+    }
+}
+
+// one window-kernel configuration: table kernel + numeric kernel
+template <class T, int NP, int SCAP, int MINB>
+static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
+{
+    const int64_t n_windows = (C->pairs + NP - 1) / NP;
+    if (n_windows > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "more than 2^37 tile pairs");
+    int32_t* win_tile = nullptr;
+    PEM_TRY(pem_alloc(ctx, &win_tile, (size_t)n_windows + 1));
+    k_window_tiles<<<pem_div_up(C->tiles + 1, 256), 256, 0, ctx->stream>>>(C->tiles, n_windows, NP, C->pair_ptr, win_tile);
+    PEM_LAUNCHED();
+    auto kern = k_step3_windows<T, NP, SCAP, MINB>;
+    constexpr int smem = S3WLayout<NP, SCAP>::BYTES;
+    static bool attr_set = false;                               // opt in to > 48 KB of dynamic shared memory (once per process)
+    if (!attr_set && smem > 48 * 1024) {
+        PEM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    KT_BEGIN(KT_NUMERIC);
+    kern<<<(unsigned)n_windows, S3W_THREADS, smem, ctx->stream>>>(
+        win_tile, C->tile_nnz_ptr, reinterpret_cast<const uint4*>(C->masks), C->pair_ptr, C->pair_list, C->pair_hit,
+        A->tile_nnz_ptr, reinterpret_cast<const T*>(A->vals), reinterpret_cast<const uint4*>(A->row_rec),
+        B->tile_nnz_ptr, reinterpret_cast<const T*>(B->vals_t), reinterpret_cast<const uint4*>(B->col_rec),
+        reinterpret_cast<T*>(C->vals));
+    KT_END(KT_NUMERIC);
+    PEM_LAUNCHED();
+    pem_free(ctx, win_tile);
+    return PEM_OK;
+}
+
+// =========================================================================================
 // PEM_OPT_OWNER = 1: SIXTEEN LANES PER C' TILE, lane = row r of the tile (two tiles per warp), paired
 // with k_step2_masks in step 2.  Lane r accumulates its C row in FOUR REGISTERS: the nonzeros of the row
 // are numbered by rank inside Cmask[r] and handled four ranks per pass.  An independent formulation of
@@ -405,23 +592,33 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
     PEM_TRY(pem_tiled_wait_vals(ctx, A));        // freshly converted operands: the values may still be on their way
     PEM_TRY(pem_tiled_wait_vals(ctx, B));
     if (C->dtype == PEM_F32 && (!C->pair_hit || !C->s3_entries))
-        return ctx->fail(PEM_ERR_ARG, "fp32 products run the default kernels only (PEM_OPT_OWNER 0 / 2)");
+        return ctx->fail(PEM_ERR_ARG, "fp32 products run the default kernels only (PEM_OPT_OWNER 0 / 2 / 4)");
     PEM_TRY(pem_alloc_bytes(ctx, (void**)&C->vals, std::max<size_t>(1, (size_t)C->nnz * pem_vsize(C->dtype))));
     const bool by_records = C->pair_hit != nullptr;         // step 2 ran the pair kernel
     // the class kernel reads every nonzero's (r, c) from Ctiles_rowColIdx; the entry-owner kernel derives it
     // from the tile mask (measured on config 4: 11.6 ms against 12.7 ms with the bytes, but producing them costs 1.0 ms)
     const bool use_rc = !C->s3_entries;
+    // default: the window kernel when C's tiles are dense enough that staging a pair's 128 bytes of records pays
+    // (at least four nonzeros per pair: stencil / FEM products), else the entry-owner kernel
+    const bool windows = by_records && C->s3_entries &&
+                         (ctx->opt_owner == 4 || (ctx->opt_owner == 0 && C->nnz >= 4 * C->pairs));
     if (C->nnz > 0 && by_records) {                          // views are cached on the handles after the first product
         PEM_TRY(pem_tiled_build_views(ctx, A, true, false));
         PEM_TRY(pem_tiled_build_views(ctx, B, false, true));
         if (use_rc) PEM_TRY(pem_result_make_rowcolidx(ctx, C));   // Ctiles_rowColIdx: every nonzero's (r, c), one byte (spgemm.cu:552-591)
     }
-    if (C->nnz > 0 && by_records && C->s3_entries) {         // entry-owner needs the first tile of each of its blocks
+    if (C->nnz > 0 && by_records && C->s3_entries && !windows) {   // entry-owner needs the first tile of each of its blocks
         const int64_t nblk = (C->nnz + S3E_ENTRIES - 1) / S3E_ENTRIES;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "C has more than 2^39 nonzeros");
         PEM_TRY(pem_alloc(ctx, &C->blk_tile, (size_t)nblk + 1));
         k_block_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->tile_nnz_ptr, C->blk_tile);
         PEM_LAUNCHED();
+    }
+    if (C->nnz > 0 && windows) {
+        PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 160, 6>(ctx, A, B, C))
+                                    : (launch_windows<double, 128, 160, 6>(ctx, A, B, C)));
+        C->stage = 3;
+        return PEM_OK;
     }
     KT_BEGIN(KT_NUMERIC);
     if (C->nnz > 0 && by_records && C->s3_entries) {

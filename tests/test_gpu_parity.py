@@ -61,7 +61,7 @@ def test_dense_blocks_all_step3_variants(engine):
         V = np.random.default_rng(n).uniform(-1, 1, n * n)
         _, _, oC = host.spgemm_from_coo(n, n, I, J, V, False)
         A = engine.convert_coo(n, n, I, J, V)
-        for owner in (0, 1, 2, 3):
+        for owner in (0, 1, 2, 3, 4):
             engine.set_option(pem.OPT_OWNER, owner)
             try:
                 C = engine.spgemm(A, A)
@@ -342,7 +342,7 @@ def test_device_pointer_input_and_pool_reuse(engine):
     A.free()
 
 
-@pytest.mark.parametrize("owner", [1, 2, 3])
+@pytest.mark.parametrize("owner", [1, 2, 3, 4])
 @pytest.mark.parametrize("k", [1, 2, 3, 4])
 def test_owner_variants_are_bit_identical(engine, k, owner):
     """PEM_OPT_OWNER = 1 (row-owner), 2 (entry-owner), 3 (tile-class kernel) must give the same bits as
@@ -626,7 +626,7 @@ def test_fuzz_all_variants_against_oracle(engine):
         A = engine.convert_coo(rows, cols, I, J, V)
         B = engine.transpose(A) if aat else A
         path = (1, 3, 4)[case % 3]
-        owner = (2, 0, 1, 3)[case % 4]
+        owner = (2, 0, 1, 3, 4)[case % 5]
         keep = case % 2
         engine.set_option(pem.OPT_STEP2_KERNEL, (1, 2, 0)[case % 3])
         engine.set_option(pem.OPT_STEP1_PATH, path)

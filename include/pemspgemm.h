@@ -92,7 +92,14 @@ typedef enum pem_option {
     PEM_OPT_ESC_VARIANT = 9,
     /* the context keeps freed device blocks for reuse; once more than this many MiB are cached they are handed
      * back to the driver (default: 80 % of the memory free at pem_ctx_create); see pem_ctx_trim */
-    PEM_OPT_CACHE_LIMIT_MB = 10
+    PEM_OPT_CACHE_LIMIT_MB = 10,
+    /* 1 (default): pem_spgemm / pem_spgemm_panel remember the sizes a product read back from the device (tile products,
+     * kept pairs, C' tiles, nnz; spgemm.cu:1169, 1246, 1291 are the reference's three such stalls) per (A, B, panel)
+     * and a repeated product of the same handles replays them: buffers are sized and grids launched from the
+     * remembered values while every kernel still computes the sizes on the device, which are compared after the
+     * product's single final synchronisation (on a mismatch the product is redone with the stalls).  0: every product
+     * stalls at its read-backs (five per product).  Setting the option clears the remembered sizes. */
+    PEM_OPT_SIZE_PLANS = 11
 } pem_option;
 
 /* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are
@@ -142,6 +149,9 @@ int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n);
 /* How step 1 of the last product ordered its tile pairs: -1 = no sort (per-row bitmap path), 0 = block-local
  * sort of every C' row in shared memory, n > 0 = n passes of the global radix sort (labels the KT slot [1]). */
 int pem_ctx_last_sort_passes(const pem_ctx* ctx);
+/* Host stalls at device-size read-backs inside products since creation (diagnostic: five per first product of an
+ * operand pair, none for its repeats under PEM_OPT_SIZE_PLANS; every product ends with one synchronisation). */
+int64_t pem_ctx_size_stalls(const pem_ctx* ctx);
 /* Allocations that missed the context's block cache and went to the CUDA pool since creation
  * (diagnostic: a steady-state loop should not add any). */
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx);

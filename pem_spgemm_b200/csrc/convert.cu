@@ -449,6 +449,7 @@ static int convert_coo_any(pem_ctx* ctx, int32_t rows, int32_t cols, int64_t nnz
     if (transpose) { int32_t t = rows; rows = cols; cols = t; }
 
     pem_tiled* T = new pem_tiled();
+    T->uid = pem_next_uid();
     T->dtype = dtype;
     T->rows = rows; T->cols = cols; T->nnz = nnz;
     T->tile_rows = (int32_t)(((int64_t)rows + PEM_TILE - 1) / PEM_TILE);
@@ -773,6 +774,7 @@ int pem_tiled_transpose(pem_ctx* ctx, const pem_tiled* A, pem_tiled** out)
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_tiled_wait_vals(ctx, A));
     pem_tiled* T = new pem_tiled();
+    T->uid = pem_next_uid();
     T->dtype = A->dtype;
     T->rows = A->cols; T->cols = A->rows; T->nnz = A->nnz;
     T->tile_rows = A->tile_cols; T->tile_cols = A->tile_rows; T->tiles = A->tiles;

@@ -102,6 +102,7 @@ int pem_ctx_create(pem_ctx** out, int device)
     uint64_t never = UINT64_MAX;
     if ((e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &never)) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost((void**)&ctx->h_scalars, PEM_NSCALARS * sizeof(int64_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMallocHost((void**)&ctx->h_check, PEM_PLAN_MAX * sizeof(int64_t))) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc((void**)&ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t))) != cudaSuccess) return bail(e);
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
@@ -132,6 +133,7 @@ void pem_ctx_destroy(pem_ctx* ctx)
         if (ev) cudaEventDestroy(ev);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_check) cudaFreeHost(ctx->h_check);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     for (auto& ev : ctx->ev_copy)
         if (ev) cudaEventDestroy(ev);
@@ -156,6 +158,10 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
             ctx->opt_owner = (int)value;
             return PEM_OK;
         case PEM_OPT_TRACE: ctx->opt_trace = (int)value; return PEM_OK;
+        case PEM_OPT_SIZE_PLANS:
+            ctx->opt_plans = value != 0;
+            ctx->plans.clear();
+            return PEM_OK;
         case PEM_OPT_ESC_VARIANT:
             if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_ESC_VARIANT must be 0..3");
             ctx->opt_esc_variant = (int)value;
@@ -200,6 +206,8 @@ int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n)
     for (int i = 0; i < KT_N; ++i) ms[i] = ctx->kt_ms[i];
     return KT_N;
 }
+
+int64_t pem_ctx_size_stalls(const pem_ctx* ctx) { return ctx ? ctx->size_stalls : 0; }
 
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx) { return ctx ? ctx->pool_mallocs : 0; }
 

@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -15,7 +16,17 @@
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
-enum { PEM_NSCALARS = 24, PEM_NEVENTS = 8 };
+enum { PEM_NSCALARS = 24, PEM_NEVENTS = 8, PEM_PLAN_MAX = 96 };
+
+// Sizes a product read back from the device (tile products, kept pairs, C' tiles, nnz ...), in program order.
+// A repeated product of the same operands replays them instead of stalling the host at every read-back: the
+// kernels still compute every size on the device, the copies are only compared after the product's final sync
+// (a mismatch cannot happen for immutable handles; if it does, the product is redone with the stalls).
+struct pem_plan {
+    int64_t v[PEM_PLAN_MAX];
+    int n = 0;
+    bool valid = false;
+};
 // pairs per block of step 2's pair kernel; step 1 (k_ctiles) emits the first tile of every such block
 constexpr int PEM_PAIR_BLOCK = 128;
 
@@ -43,6 +54,13 @@ struct pem_ctx {
     int sm_count = 148;
     int smem_optin = 227 * 1024; // max dynamic shared memory per block
     int64_t* h_scalars = nullptr; // pinned, PEM_NSCALARS entries: size read-backs
+    int64_t* h_check = nullptr;   // pinned, PEM_PLAN_MAX entries: the same read-backs of a replayed product, compared at its end
+    std::map<std::vector<int64_t>, pem_plan> plans;   // key: operand ids, panel, options that change sizes
+    pem_plan* plan = nullptr;     // plan of the product in flight (pem_spgemm_panel only; stage-level calls stall)
+    bool plan_replay = false;
+    int plan_pos = 0;
+    int opt_plans = 1;            // PEM_OPT_SIZE_PLANS
+    int64_t size_stalls = 0;      // host stalls at size read-backs since creation (pem_ctx_size_stalls)
     int64_t* d_scalars = nullptr; // device mirror the kernels reduce into
     cudaEvent_t ev[PEM_NEVENTS] = {};
     cudaEvent_t kev[2 * KT_N] = {};   // begin/end pairs of the individually timed kernels
@@ -115,6 +133,12 @@ static inline void pem_free(pem_ctx* ctx, T*& p)
     p = nullptr;
 }
 
+static inline uint64_t pem_next_uid()
+{
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
+}
+
 static inline int pem_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------
@@ -127,6 +151,7 @@ enum { PEM_F64 = 0, PEM_F32 = 1 };
 static inline size_t pem_vsize(int dtype) { return dtype == PEM_F32 ? 4 : 8; }
 
 struct pem_tiled {
+    uint64_t uid = 0;                 // unique per conversion (handles are immutable): key of the size plans
     int dtype = PEM_F64;
     int32_t rows = 0, cols = 0;
     int64_t nnz = 0;
@@ -199,6 +224,40 @@ enum {
     SC_NSMALL1 = 9, SC_NLARGE1 = 10,  // step 1: rows per kernel-2 list
     SC_NSMALL2 = 11, SC_NLARGE2 = 12, // step 1: rows per kernel-3 list
     SC_WORK0 = 16                     // step 1: four work-queue cursors (count large/small, fill large/small)
+};
+
+// One host read-back of device-side sizes: add() enqueues copies, get() returns the values: after a stream
+// synchronisation, or, when the product in flight replays a plan, immediately from the plan.
+struct pem_size_read {
+    pem_ctx* ctx;
+    int n = 0;
+    explicit pem_size_read(pem_ctx* c) : ctx(c) {}
+    bool replay() const { return ctx->plan && ctx->plan_replay; }
+    int add(const int64_t* d_src, int cnt)
+    {
+        if (n + cnt > PEM_NSCALARS || (ctx->plan && ctx->plan_pos + n + cnt > PEM_PLAN_MAX))
+            return ctx->fail(PEM_ERR_LIMIT, "size read-back overflow");
+        int64_t* dst = replay() ? ctx->h_check + ctx->plan_pos + n : ctx->h_scalars + n;
+        PEM_CK(cudaMemcpyAsync(dst, d_src, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        n += cnt;
+        return PEM_OK;
+    }
+    int get(int64_t* out)
+    {
+        if (replay()) {
+            if (ctx->plan_pos + n > ctx->plan->n) return ctx->fail(PEM_ERR_ARG, "size plan out of step");
+            for (int i = 0; i < n; ++i) out[i] = ctx->plan->v[ctx->plan_pos + i];
+        } else {
+            PEM_CK(cudaStreamSynchronize(ctx->stream));
+            ++ctx->size_stalls;
+            for (int i = 0; i < n; ++i) out[i] = ctx->h_scalars[i];
+            if (ctx->plan)
+                for (int i = 0; i < n; ++i) ctx->plan->v[ctx->plan_pos + i] = out[i];
+        }
+        if (ctx->plan) ctx->plan_pos += n;
+        n = 0;
+        return PEM_OK;
+    }
 };
 
 // step entry points implemented in spgemm.cu / convert.cu / export.cu

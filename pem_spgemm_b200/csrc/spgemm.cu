@@ -419,9 +419,11 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
         ctx->launches += 2;
         pem_free(ctx, tmp);
     }
-    PEM_CK(cudaMemcpyAsync(ctx->h_scalars, C->tile_nnz_ptr + C->tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PEM_CK(cudaStreamSynchronize(ctx->stream));
-    C->nnz = ctx->h_scalars[0];
+    {
+        pem_size_read rd(ctx);
+        PEM_TRY(rd.add(C->tile_nnz_ptr + C->tiles, 1));
+        PEM_TRY(rd.get(&C->nnz));
+    }
     C->stage = 2;
     // step-3 mapping (step3.cu): the entry-owner kernel unless the tile-class kernel is asked for
     C->s3_entries = ctx->opt_owner != 3;
@@ -454,17 +456,54 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
     PEM_CK(cudaStreamSynchronize(ctx->stream));
     auto w0 = std::chrono::high_resolution_clock::now();
     pem_result* C = nullptr;
-    for (int i = 0; i < KT_N; ++i) { ctx->kt_seen[i] = false; ctx->kt_ms[i] = 0.0; }
-    PEM_CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    PEM_TRY(pem_step1_symbolic(ctx, A, B, rb, re, &C));
-    cudaEventRecord(ctx->ev[3], ctx->stream);
-    int rc = pem_step2_symbolic(ctx, A, B, C);
-    cudaEventRecord(ctx->ev[4], ctx->stream);
-    if (rc == PEM_OK) rc = pem_step3_numeric(ctx, A, B, C);
-    cudaEventRecord(ctx->ev[5], ctx->stream);
-    if (rc == PEM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-        rc = ctx->fail_cuda(cudaGetLastError(), "cudaStreamSynchronize after step 3", __FILE__, __LINE__);
-    if (rc != PEM_OK) { pem_result_free(ctx, C); return rc; }
+    // size plan of this (A, B, panel): recorded by the first product, replayed (no host stall before the final
+    // synchronisation) by every later one
+    const std::vector<int64_t> key = {(int64_t)A->uid, (int64_t)B->uid, rb, re, ctx->opt_keep_empty, ctx->opt_step1_path,
+                                      ctx->opt_esc_variant};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ctx->plan = nullptr;
+        ctx->plan_replay = false;
+        ctx->plan_pos = 0;
+        if (ctx->opt_plans) {
+            if (ctx->plans.size() > 256) ctx->plans.clear();
+            pem_plan& pl = ctx->plans[key];
+            ctx->plan = &pl;
+            ctx->plan_replay = pl.valid;
+        }
+        for (int i = 0; i < KT_N; ++i) { ctx->kt_seen[i] = false; ctx->kt_ms[i] = 0.0; }
+        PEM_CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        int rc = pem_step1_symbolic(ctx, A, B, rb, re, &C);
+        cudaEventRecord(ctx->ev[3], ctx->stream);
+        if (rc == PEM_OK) rc = pem_step2_symbolic(ctx, A, B, C);
+        cudaEventRecord(ctx->ev[4], ctx->stream);
+        if (rc == PEM_OK) rc = pem_step3_numeric(ctx, A, B, C);
+        cudaEventRecord(ctx->ev[5], ctx->stream);
+        if (rc == PEM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = ctx->fail_cuda(cudaGetLastError(), "cudaStreamSynchronize after step 3", __FILE__, __LINE__);
+        pem_plan* pl = ctx->plan;
+        const bool replayed = ctx->plan_replay;
+        const int npos = ctx->plan_pos;
+        ctx->plan = nullptr;
+        ctx->plan_replay = false;
+        if (rc != PEM_OK) {
+            if (pl) ctx->plans.erase(key);
+            pem_result_free(ctx, C);
+            return rc;
+        }
+        if (!pl) break;
+        if (!replayed) {
+            pl->n = npos;
+            pl->valid = true;
+            break;
+        }
+        bool same = npos == pl->n;
+        for (int i = 0; same && i < npos; ++i) same = ctx->h_check[i] == pl->v[i];
+        if (same) break;
+        ctx->plans.erase(key);                      // never expected: redo the product with the stalls
+        pem_result_free(ctx, C);
+        C = nullptr;
+        if (attempt == 1) return ctx->fail(PEM_ERR_CUDA, "sizes changed under a replayed size plan");
+    }
     auto w1 = std::chrono::high_resolution_clock::now();
     for (int i = 0; i < KT_N; ++i) {
         float ms = 0.f;

@@ -574,11 +574,13 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
             rb, re, A->tile_row_ptr, A->tile_col_idx, B->tile_row_ptr, B->tile_col_idx, win, l1s, l1l, key_l, ctx->d_scalars);
         ++ctx->launches;
         S_CK(cudaGetLastError());
-        S_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        S_CK(cudaStreamSynchronize(ctx->stream));
-        maxwin = ctx->h_scalars[SC_MAXWIN];
-        C->tile_products = ctx->h_scalars[SC_SUMP];
-        n1s = ctx->h_scalars[SC_NSMALL1]; n1l = ctx->h_scalars[SC_NLARGE1];
+        int64_t sc[PEM_NSCALARS];
+        pem_size_read rd(ctx);
+        S_TRY(rd.add(ctx->d_scalars + SC_MAXWIN, SC_NLARGE2 - SC_MAXWIN + 1));   // the computed sizes only (not the work-queue cursors)
+        S_TRY(rd.get(sc + SC_MAXWIN));
+        maxwin = sc[SC_MAXWIN];
+        C->tile_products = sc[SC_SUMP];
+        n1s = sc[SC_NSMALL1]; n1l = sc[SC_NLARGE1];
     }
     // shared-memory plan (dynamic part; the kernels also hold the staging area / sort slabs and a
     // few words statically, which count against the same 227 KB)
@@ -621,12 +623,14 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
         S_TRY(pem_scan_exclusive_i64(ctx, pair_row_ptr, (int64_t)nrows + 1));
         S_CK(cudaMemcpyAsync(&ctx->d_scalars[SC_T0], C->row_ptr + nrows, 8, cudaMemcpyDeviceToDevice, ctx->stream));
         S_CK(cudaMemcpyAsync(&ctx->d_scalars[SC_T1], pair_row_ptr + nrows, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        S_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        S_CK(cudaStreamSynchronize(ctx->stream));
-        C->tiles = ctx->h_scalars[SC_T0];
-        C->pairs = ctx->h_scalars[SC_T1];
-        maxd = ctx->h_scalars[SC_MAXD];
-        n2s = ctx->h_scalars[SC_NSMALL2]; n2l = ctx->h_scalars[SC_NLARGE2];
+        int64_t sc[PEM_NSCALARS];
+        pem_size_read rd(ctx);
+        S_TRY(rd.add(ctx->d_scalars + SC_MAXWIN, SC_NLARGE2 - SC_MAXWIN + 1));   // the computed sizes only (not the work-queue cursors)
+        S_TRY(rd.get(sc + SC_MAXWIN));
+        C->tiles = sc[SC_T0];
+        C->pairs = sc[SC_T1];
+        maxd = sc[SC_MAXD];
+        n2s = sc[SC_NSMALL2]; n2l = sc[SC_NLARGE2];
     }
     S_TRY(pem_alloc(ctx, &C->tile_row, (size_t)C->tiles));
     S_TRY(pem_alloc(ctx, &C->tile_col, (size_t)C->tiles));

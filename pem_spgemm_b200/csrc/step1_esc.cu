@@ -468,7 +468,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     // (PEM_OPT_ESC_VARIANT bit 0 forces the count-then-write variant; tests use it, nothing else should)
     bool staged = !(ctx->opt_esc_variant & 1) &&
                   staged_bytes <= std::max<size_t>((free_b + ctx->cached_bytes) / 3, (size_t)1 << 28);
-    int64_t F = 0;
+    int64_t F = 0, longest_row = 0;
     if (staged && (pem_alloc(ctx, &key_b, (size_t)P) != PEM_OK || pem_alloc(ctx, &val_b, (size_t)P) != PEM_OK)) {
         pem_free(ctx, key_b);              // the books were too optimistic (another process on the GPU?): count first
         pem_free(ctx, val_b);
@@ -508,10 +508,15 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
             k_max_segment<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, seg_off, ctx->d_scalars);
             E_LAUNCHED();
         }
-        E_CK(cudaMemcpyAsync(ctx->h_scalars, d_F, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        E_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        E_CK(cudaStreamSynchronize(ctx->stream));
-        F = ctx->h_scalars[0];
+        {
+            pem_size_read rd(ctx);
+            int64_t v[2];
+            E_TRY(rd.add(d_F, 1));
+            E_TRY(rd.add(ctx->d_scalars + SC_MAXD, 1));
+            E_TRY(rd.get(v));
+            F = v[0];
+            longest_row = v[1];
+        }
         tr.mark("expand + compact done, F and the longest row known");
         C->pairs = F;
         if (F == 0) {
@@ -519,9 +524,11 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
             return PEM_OK;
         }
     } else {
-        E_CK(cudaMemcpyAsync(ctx->h_scalars, d_F, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        E_CK(cudaStreamSynchronize(ctx->stream));
-        F = ctx->h_scalars[0];
+        {
+            pem_size_read rd(ctx);
+            E_TRY(rd.add(d_F, 1));
+            E_TRY(rd.get(&F));
+        }
         tr.mark("count pass done, F known");
         C->pairs = F;
         if (F == 0) {
@@ -544,12 +551,15 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
             k_max_segment<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, seg_off, ctx->d_scalars);
             E_LAUNCHED();
         }
-        E_CK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->d_scalars + SC_MAXD, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        E_CK(cudaStreamSynchronize(ctx->stream));
+        {
+            pem_size_read rd(ctx);
+            E_TRY(rd.add(ctx->d_scalars + SC_MAXD, 1));
+            E_TRY(rd.get(&longest_row));
+        }
     }
     // (a 1024-thread block sorting up to 32768 pairs of a row was tried for config 3's ~13 K-pair rows:
     //  4.5 ms against 2.7 ms for the radix sort)
-    const int by_rows = consider_rows && ctx->h_scalars[1] <= RS_SMALL ? 1 : 0;       // 1: every row holds <= 1024 pairs
+    const int by_rows = consider_rows && longest_row <= RS_SMALL ? 1 : 0;       // 1: every row holds <= 1024 pairs
     ctx->last_sort_passes = by_rows ? 0 : (wbits + rbits + 7) / 8;
     if (by_rows) {
         KT_BEGIN(KT_SORT);
@@ -574,6 +584,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     pem_free(ctx, key_b);
     pem_free(ctx, val_b);
     // heads of the equal-key runs = C' tiles
+    int64_t T = 0;
     E_TRY(pem_alloc(ctx, &heads, (size_t)F));
     {
         size_t tb = 0;
@@ -585,10 +596,10 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         E_CK(cub::DeviceSelect::If(tmp, tb, iota, heads, d_n, F, pred, ctx->stream));
         ctx->launches += 2;
         pem_free(ctx, tmp);
-        E_CK(cudaMemcpyAsync(ctx->h_scalars, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        E_CK(cudaStreamSynchronize(ctx->stream));
+        pem_size_read rd(ctx);
+        E_TRY(rd.add(d_n, 1));
+        E_TRY(rd.get(&T));
     }
-    const int64_t T = ctx->h_scalars[0];
     if (T >= 0x7fffffffLL) {
         cleanup();
         return ctx->fail(PEM_ERR_LIMIT, "more than 2^31 C' tiles in one result: multiply in tile-row panels (pem_spgemm_panel)");
@@ -674,11 +685,15 @@ int pem_step1_esc(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_resu
     k_max_window<<<pem_div_up(nrows, 256), 256, 0, ctx->stream>>>(nrows, jmin, jmax, pptr, np, ctx->d_scalars);
     ++ctx->launches;
     E_CK(cudaGetLastError());
-    E_CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, PEM_NSCALARS * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    E_CK(cudaStreamSynchronize(ctx->stream));
-    const int64_t P_tile = ctx->h_scalars[SC_SUMP];
-    const int64_t P_sliced = ctx->h_scalars[SC_T2], n_items = ctx->h_scalars[SC_T1];
-    const int64_t maxw = ctx->h_scalars[SC_MAXWIN];
+    int64_t sc[PEM_NSCALARS];
+    {
+        pem_size_read rd(ctx);                      // stall 1 of a first product (none when a size plan is replayed)
+        E_TRY(rd.add(ctx->d_scalars + SC_MAXWIN, SC_NLARGE2 - SC_MAXWIN + 1));   // the computed sizes only (not the work-queue cursors)
+        E_TRY(rd.get(sc + SC_MAXWIN));
+    }
+    const int64_t P_tile = sc[SC_SUMP];
+    const int64_t P_sliced = sc[SC_T2], n_items = sc[SC_T1];
+    const int64_t maxw = sc[SC_MAXWIN];
     C->tile_products = P_tile;
     int rc = PEM_OK;
     if (P_tile > 0) {

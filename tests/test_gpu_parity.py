@@ -342,6 +342,59 @@ def test_device_pointer_input_and_pool_reuse(engine):
     A.free()
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("step1_path", [0, 1, 2])
+def test_size_plans_replay_without_stalls(engine, k, step1_path):
+    """PEM_OPT_SIZE_PLANS: the first product of an operand pair stalls at its size read-backs (the reference's
+    spgemm.cu:1169, 1246, 1291) and records them; repeats of the same handles (whole product and panels) replay the
+    sizes, stall nowhere before their final synchronisation and give the same bits; other operands get their own plan."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    engine.set_option(pem.OPT_STEP1_PATH, step1_path)
+    engine.set_option(pem.OPT_SIZE_PLANS, 1)          # also clears the remembered sizes
+    try:
+        s0 = engine.size_stalls
+        C = engine.spgemm(A, B)
+        first = engine.size_stalls - s0
+        assert first >= 3
+        _assert_same_C(C, oC)
+        C.free()
+        for _ in range(3):
+            s1 = engine.size_stalls
+            C = engine.spgemm(A, B)
+            assert engine.size_stalls == s1           # replayed
+            _assert_same_C(C, oC)
+            C.free()
+        bounds = engine.partition_panels(A, B, 2)
+        for rep in range(2):
+            s1 = engine.size_stalls
+            parts = [engine.spgemm(A, B, panel=(int(bounds[i]), int(bounds[i + 1]))) for i in range(2)]
+            assert (engine.size_stalls == s1) == (rep == 1)
+            assert sum(p.info.nnz for p in parts) == oC.nnz
+            for p_ in parts:
+                p_.free()
+        # a second conversion of the same matrix is a different handle: its own plan, recorded again
+        A2 = engine.convert_coo(rows, cols, I, J, V)
+        s1 = engine.size_stalls
+        C = engine.spgemm(A2, B)
+        assert engine.size_stalls - s1 == first
+        _assert_same_C(C, oC)
+        C.free(); A2.free()
+        engine.set_option(pem.OPT_SIZE_PLANS, 0)
+        s1 = engine.size_stalls
+        C = engine.spgemm(A, B)
+        assert engine.size_stalls - s1 == first
+        C.free()
+    finally:
+        engine.set_option(pem.OPT_SIZE_PLANS, 1)
+        engine.set_option(pem.OPT_STEP1_PATH, 0)
+    A.free()
+    if B is not A:
+        B.free()
+
+
 @pytest.mark.parametrize("owner", [1, 2, 3, 4])
 @pytest.mark.parametrize("k", [1, 2, 3, 4])
 def test_owner_variants_are_bit_identical(engine, k, owner):

@@ -55,7 +55,10 @@ typedef enum pem_option {
      * tile-column window that fits shared memory) where the per-row bitmap path has fewer launches;
      * 1 = force the per-row windowed bitmap accumulator (the reference's SPA idea,
      * spgemm.cu:271-384); 2 = force expand-sort-compress; 3 / 4 = expand-sort-compress with the
-     * tile-level / row-sliced product expansion forced (2 picks the one with fewer products).  Replaces the reference's global switch between
+     * tile-level / row-sliced product expansion forced (2 picks the one with fewer products); 5 = the per-row path with
+     * HASH accumulators (open addressing in shared memory, the NSPARSE idea) on every tile row of at most 1024 tile
+     * products and the bitmap on the others (1 / automatic use the hash only on rows whose window of tile columns is
+     * more than 16 x wider than their products).  Replaces the reference's global switch between
      * SPA and NSPARSE hashing `B_tileCols > 512*32` (spgemm.cu:1142). */
     PEM_OPT_STEP1_PATH = 2,
     /* thread mapping of step 3 (and of step 2 for value 1).  Results are bit-identical.

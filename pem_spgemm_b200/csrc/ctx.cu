@@ -150,7 +150,7 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
     switch (option) {
         case PEM_OPT_KEEP_EMPTY_TILES: ctx->opt_keep_empty = value != 0; return PEM_OK;
         case PEM_OPT_STEP1_PATH:
-            if (value < 0 || value > 4) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP1_PATH must be 0..4");
+            if (value < 0 || value > 5) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP1_PATH must be 0..5");
             ctx->opt_step1_path = (int)value;
             return PEM_OK;
         case PEM_OPT_OWNER:

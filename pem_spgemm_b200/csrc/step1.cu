@@ -48,6 +48,46 @@ constexpr int LARGE_LA = 512;         // ... or this many A tiles
 constexpr int SORT_MAX = 12;          // pair lists up to this length: insertion sort by one thread
 constexpr int WSORT_MAX = 256;        // ... up to this length: rank sort by one warp; longer: block rebuild
 constexpr int UNROLL = 4;             // independent product loads in flight per thread
+// Hash accumulator (the reference's NSPARSE idea, NSPARSE/spgemm_nsparse_kernel.h:464-687, 910-1119): a tile row
+// whose products are few but spread over a wide window of tile columns does not clear, scan and popcount a bitmap
+// of the whole window; its tile columns go into an open-addressing table in shared memory sized by the row's
+// products (linear probing, atomicCAS), the distinct columns are compacted and sorted, and a product finds its
+// C' tile by binary search among them.
+constexpr int HASH_MAXP = 1024;       // rows with at most this many tile products can take the hash accumulator
+constexpr int HASH_SLOTS = 2 * HASH_MAXP;
+constexpr int HASH_SPREAD = 16;       // ... automatically when the window holds more than this many columns per product
+
+__device__ __forceinline__ int hash_slots(unsigned P)      // power of two >= 2 * P, at least 64
+{
+    return max(64, 1 << (33 - __clz(max(P, 1u) - 1u | 1u)));
+}
+// inserts tile column j; true when it was not in the table yet
+__device__ __forceinline__ bool hash_insert(int* tab, int H, int j)
+{
+    unsigned h = ((unsigned)j * 2654435761u) >> (__clz(H) + 1);
+    for (;;) {
+        const int old = atomicCAS(&tab[h], -1, j);
+        if (old == -1) return true;
+        if (old == j) return false;
+        h = (h + 1) & (unsigned)(H - 1);
+    }
+}
+// ascending bitonic sort of a[0..n2) (n2 a power of two) by the whole block
+template <int THREADS>
+__device__ __forceinline__ void block_bitonic(int* a, int n2)
+{
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += THREADS) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const int u = a[i], v = a[x];
+                    if ((u > v) == ((i & k) == 0)) { a[i] = v; a[x] = u; }
+                }
+            }
+            __syncthreads();
+        }
+}
 
 template <int THREADS>
 __device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* red)
@@ -173,7 +213,7 @@ __global__ void __launch_bounds__(256)
 k_row_window(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __restrict__ Acol,
              const int32_t* __restrict__ Brp, const int32_t* __restrict__ Bcol,
              int2* __restrict__ win, int32_t* __restrict__ list_small, int32_t* __restrict__ list_large,
-             unsigned* __restrict__ key_large, int64_t* __restrict__ scalars)
+             unsigned* __restrict__ key_large, int64_t* __restrict__ scalars, int hash_mode)
 {
     int row = rb + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (row >= re) return;
@@ -197,13 +237,19 @@ k_row_window(int rb, int re, const int32_t* __restrict__ Arp, const int32_t* __r
         P += __shfl_xor_sync(0xffffffffu, P, o);
     }
     if (lane == 0) {
-        win[row - rb] = make_int2(jmin, jmax);
+        const long long words = jmax >= 0 ? ((jmax - (jmin & ~31)) >> 5) + 1 : 0;
+        const bool heavy = (long long)P > LARGE_P || ae - as > LARGE_LA;
+        // accumulator of this row: hash table (hash_mode 1: whenever it fits; 0: when the window is wide for the
+        // row's products) or windowed bitmap.  A hash row is marked by a window end below -1 (-jmax - 2).
+        const bool hashed = jmax >= 0 && !heavy && P <= (unsigned long long)HASH_MAXP &&
+                            (hash_mode == 1 || (hash_mode == 0 && words * 32 > (long long)HASH_SPREAD * (long long)P));
+        win[row - rb] = make_int2(jmin, hashed ? -jmax - 2 : jmax);
         if (jmax >= 0) {
-            long long words = ((jmax - (jmin & ~31)) >> 5) + 1;
-            atomicMax((long long*)&scalars[SC_MAXWIN], words);
+            if (hashed) atomicMax((long long*)&scalars[SC_T2], 1ll);
+            else atomicMax((long long*)&scalars[SC_MAXWIN], words);
             atomicMax((long long*)&scalars[SC_MAXP], (long long)P);
             atomicAdd((unsigned long long*)&scalars[SC_SUMP], P);
-            if ((long long)P > LARGE_P || ae - as > LARGE_LA) {
+            if (heavy) {
                 const unsigned long long at = atomicAdd((unsigned long long*)&scalars[SC_NLARGE1], 1ull);
                 list_large[at] = row;
                 key_large[at] = ~(unsigned)min(P, 0xFFFFFFFFull);   // ascending sort = heaviest first
@@ -243,19 +289,37 @@ k_step1_count(const int32_t* __restrict__ rows, int nrows_list, int rb,
         if (li >= nrows_list) break;
         const int row = rows[li];
         const int2 wnd = win[row - rb];
-        const int base = wnd.x & ~31;
-        const int W = ((wnd.y - base) >> 5) + 1;
-        for (int w = tid; w < W; w += THREADS) sm[w] = 0;
-        __syncthreads();
-        unsigned f = 0;
-        for_each_product<THREADS>(st, red, Arp[row], Arp[row + 1], Acol, AcolOcc, Brp, Bcol, BrowOcc, keep_empty,
-                                  [&](int, int, int j) {
-                                      j -= base;
-                                      atomicOr(&sm[j >> 5], 1u << (j & 31));
-                                      ++f;
-                                  });
-        unsigned d = 0;
-        for (int w = tid; w < W; w += THREADS) d += __popc(sm[w]);
+        unsigned f = 0, d = 0;
+        if (wnd.y < -1) {                           // hash accumulator: distinct tile columns counted at insertion
+            int* tab = reinterpret_cast<int*>(sm);
+            const int as = Arp[row], ae = Arp[row + 1];
+            unsigned P = 0;
+            for (int p = as + tid; p < ae; p += THREADS) {
+                const int k = Acol[p];
+                P += (unsigned)(Brp[k + 1] - Brp[k]);
+            }
+            P = block_sum<THREADS>(P, red);
+            const int H = hash_slots(P);
+            for (int w = tid; w < H; w += THREADS) tab[w] = -1;
+            __syncthreads();
+            for_each_product<THREADS>(st, red, as, ae, Acol, AcolOcc, Brp, Bcol, BrowOcc, keep_empty,
+                                      [&](int, int, int j) {
+                                          d += hash_insert(tab, H, j) ? 1u : 0u;
+                                          ++f;
+                                      });
+        } else {
+            const int base = wnd.x & ~31;
+            const int W = ((wnd.y - base) >> 5) + 1;
+            for (int w = tid; w < W; w += THREADS) sm[w] = 0;
+            __syncthreads();
+            for_each_product<THREADS>(st, red, Arp[row], Arp[row + 1], Acol, AcolOcc, Brp, Bcol, BrowOcc, keep_empty,
+                                      [&](int, int, int j) {
+                                          j -= base;
+                                          atomicOr(&sm[j >> 5], 1u << (j & 31));
+                                          ++f;
+                                      });
+            for (int w = tid; w < W; w += THREADS) d += __popc(sm[w]);
+        }
         d = block_sum<THREADS>(d, red);
         f = block_sum<THREADS>(f, red);
         if (tid == 0 && d > 0) {
@@ -318,9 +382,18 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
         const int64_t pbase = pair_row_ptr[row - rb];
         const int F = (int)(pair_row_ptr[row - rb + 1] - pbase);
         const int2 wnd = win[row - rb];
-        const int base = wnd.x & ~31;
-        const int W = ((wnd.y - base) >> 5) + 1;
+        const bool hashed = wnd.y < -1;             // hash accumulator: table in the bitmap's place, sorted columns behind it
+        const int base = hashed ? 0 : wnd.x & ~31;
+        const int W = hashed ? 0 : ((wnd.y - base) >> 5) + 1;
+        int* tab = reinterpret_cast<int*>(sm);
+        int* cols = tab;                            // hash rows: set below (behind the table)
+        int H = 0;
         unsigned* cnt = (D <= dcap) ? sm + 2 * (size_t)Wmax : gscratch + (size_t)blockIdx.x * gstride;
+        if (hashed) {
+            H = hash_slots((unsigned)F);            // F kept products <= the row's products: 2 * F slots hold them
+            cols = tab + H;
+            for (int w = tid; w < H; w += THREADS) tab[w] = -1;
+        }
         for (int w = tid; w < W; w += THREADS) bitmap[w] = 0;
         for (int i = tid; i < D; i += THREADS) cnt[i] = 0;
         if (tid == 0) cursor = 0;
@@ -333,7 +406,8 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
         for_each_product<THREADS>(u.st, red, as, ae, Acol, AcolOcc, Brp, Bcol, BrowOcc, keep_empty,
                                   [&](int p, int q, int j) {
                                       j -= base;
-                                      atomicOr(&bitmap[j >> 5], 1u << (j & 31));
+                                      if (hashed) hash_insert(tab, H, j);
+                                      else atomicOr(&bitmap[j >> 5], 1u << (j & 31));
                                       // warp-aggregated slot claim
                                       const unsigned act = __activemask();
                                       const int leader = __ffs(act) - 1;
@@ -343,13 +417,37 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
                                       tpq[slot] = make_int2(p, q); tj[slot] = j;
                                   });
         PROF_MARK(0);
-        block_scan_exclusive<THREADS>(prefix, W, [&](int i) { return (unsigned)__popc(bitmap[i]); }, red);
+        if (hashed) {
+            // the table's D distinct columns, compacted behind it and sorted ascending (padded to a power of two)
+            int D2 = 1;
+            while (D2 < D) D2 <<= 1;
+            if (tid == 0) cursor = 0;
+            __syncthreads();
+            for (int w = tid; w < H; w += THREADS) {
+                const int j = tab[w];
+                if (j >= 0) cols[atomicAdd(&cursor, 1u)] = j;
+            }
+            for (int i = D + tid; i < D2; i += THREADS) cols[i] = INT_MAX;
+            __syncthreads();
+            block_bitonic<THREADS>(cols, D2);
+        } else
+            block_scan_exclusive<THREADS>(prefix, W, [&](int i) { return (unsigned)__popc(bitmap[i]); }, red);
         PROF_MARK(1);
         // pass B: pairs per C' tile; the list's j is replaced by its rank
         for (int i = tid; i < F; i += THREADS) {
             const int j = tj[i];
-            const int w = j >> 5;
-            const unsigned rank = prefix[w] + __popc(bitmap[w] & ((1u << (j & 31)) - 1u));
+            unsigned rank;
+            if (hashed) {                           // position of j among the sorted columns
+                int lo = 0, hi = D - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cols[mid] < j) lo = mid + 1; else hi = mid;
+                }
+                rank = (unsigned)lo;
+            } else {
+                const int w = j >> 5;
+                rank = prefix[w] + __popc(bitmap[w] & ((1u << (j & 31)) - 1u));
+            }
             tj[i] = (int)rank;
             atomicAdd(&cnt[rank], 1u);
         }
@@ -358,6 +456,12 @@ k_step1_fill(const int32_t* __restrict__ rows, int nrows_list, int rb,
         block_scan_exclusive<THREADS>(cnt, D, [&](int i) { return cnt[i]; }, red);
         PROF_MARK(3);
         // emit the C' tiles of this row (columns ascending) with their pair offsets
+        if (hashed)
+            for (int r = tid; r < D; r += THREADS) {
+                c_tile_row[cbase + r] = row;
+                c_tile_col[cbase + r] = cols[r];
+                pair_ptr[cbase + r] = pbase + cnt[r];
+            }
         for (int w = tid; w < W; w += THREADS) {
             unsigned m = bitmap[w];
             unsigned r = prefix[w];
@@ -517,7 +621,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     // small operands are launch-bound: the per-row bitmap path below needs ~8 launches and 2 host
     // syncs, expand-sort-compress ~20 and 3
     const bool small = (int64_t)A->tiles + B->tiles <= 65536 && B->tile_cols <= 65536;
-    if (ctx->opt_step1_path >= 2 || (ctx->opt_step1_path == 0 && !small)) {     // expand-sort-compress (step1_esc.cu)
+    if ((ctx->opt_step1_path >= 2 && ctx->opt_step1_path != 5) || (ctx->opt_step1_path == 0 && !small)) {     // expand-sort-compress (step1_esc.cu)
         int rc = pem_alloc(ctx, &C->row_ptr, (size_t)nrows + 1);
         if (rc == PEM_OK) rc = pem_step1_esc(ctx, A, B, C);
         if (rc != PEM_OK) { pem_result_free(ctx, C); return rc; }
@@ -570,8 +674,11 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
     const bool any = nrows > 0 && A->tiles > 0 && B->tiles > 0;
     int64_t maxwin = 0, maxd = 0, n1s = 0, n1l = 0, n2s = 0, n2l = 0;
     if (any) {
+        // PEM_OPT_STEP1_PATH 5: hash accumulators wherever a row's products fit the table; 1 / automatic: only for rows
+        // whose window is wide for their products
         k_row_window<<<pem_div_up((int64_t)nrows * 32, 256), 256, 0, ctx->stream>>>(
-            rb, re, A->tile_row_ptr, A->tile_col_idx, B->tile_row_ptr, B->tile_col_idx, win, l1s, l1l, key_l, ctx->d_scalars);
+            rb, re, A->tile_row_ptr, A->tile_col_idx, B->tile_row_ptr, B->tile_col_idx, win, l1s, l1l, key_l, ctx->d_scalars,
+            ctx->opt_step1_path == 5 ? 1 : 0);
         ++ctx->launches;
         S_CK(cudaGetLastError());
         int64_t sc[PEM_NSCALARS];
@@ -579,6 +686,7 @@ extern "C" int pem_step1_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_ti
         S_TRY(rd.add(ctx->d_scalars + SC_MAXWIN, SC_NLARGE2 - SC_MAXWIN + 1));   // the computed sizes only (not the work-queue cursors)
         S_TRY(rd.get(sc + SC_MAXWIN));
         maxwin = sc[SC_MAXWIN];
+        if (sc[SC_T2]) maxwin = std::max<int64_t>(maxwin, HASH_SLOTS);     // hash rows: table (and sorted columns) in the bitmap's place
         C->tile_products = sc[SC_SUMP];
         n1s = sc[SC_NSMALL1]; n1l = sc[SC_NLARGE1];
     }

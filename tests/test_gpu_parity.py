@@ -197,7 +197,7 @@ def test_conversion_input_errors(engine):
 
 
 # 3: expand-sort-compress at tile level, 4: ... through B's row slices, 1: windowed bitmap SPA (0/2 pick one of them)
-@pytest.mark.parametrize("step1_path", [3, 4, 1])
+@pytest.mark.parametrize("step1_path", [3, 4, 1, 5])
 @pytest.mark.parametrize("keep_empty", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_steps_match_tile_oracle(engine, k, keep_empty, step1_path):
@@ -343,7 +343,7 @@ def test_device_pointer_input_and_pool_reuse(engine):
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
-@pytest.mark.parametrize("step1_path", [0, 1, 2])
+@pytest.mark.parametrize("step1_path", [0, 1, 2, 5])
 def test_size_plans_replay_without_stalls(engine, k, step1_path):
     """PEM_OPT_SIZE_PLANS: the first product of an operand pair stalls at its size read-backs (the reference's
     spgemm.cu:1169, 1246, 1291) and records them; repeats of the same handles (whole product and panels) replay the
@@ -473,6 +473,29 @@ def test_step3_tile_classes_are_bit_identical(engine, k, small_e, small_np):
         engine.set_option(pem.OPT_OWNER, 0)
         engine.set_option(pem.OPT_S3_SMALL_NNZ, 8)
         engine.set_option(pem.OPT_S3_SMALL_PAIRS, 64)
+    if B is not A:
+        B.free()
+    A.free()
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_step1_hash_rows_agree_at_full_size(engine, k):
+    """PEM_OPT_STEP1_PATH = 5 (hash accumulators on every tile row of at most 1024 products, bitmap on the hub
+    rows) against expand-sort-compress at BASELINE.json sizes: identical C' structure, pair lists and value bits."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
+    engine.set_option(pem.OPT_STEP1_PATH, 2)
+    try:
+        C0 = engine.spgemm(A, B)
+        engine.set_option(pem.OPT_STEP1_PATH, 5)
+        C1 = engine.spgemm(A, B)
+    finally:
+        engine.set_option(pem.OPT_STEP1_PATH, 0)
+    assert (C0.info.tiles, C0.info.pairs, C0.info.nnz) == (C1.info.tiles, C1.info.pairs, C1.info.nnz)
+    for name in ("row_ptr", "tile_row", "tile_col", "pair_ptr", "pairs_a", "pairs_b", "tile_nnz_ptr", "vals"):
+        assert np.array_equal(C0.array(name), C1.array(name)), name
+    C0.free(); C1.free()
     if B is not A:
         B.free()
     A.free()
@@ -678,7 +701,7 @@ def test_fuzz_all_variants_against_oracle(engine):
         ro, co, vo = oC.to_coo()
         A = engine.convert_coo(rows, cols, I, J, V)
         B = engine.transpose(A) if aat else A
-        path = (1, 3, 4)[case % 3]
+        path = (1, 3, 4, 5)[case % 4]
         owner = (2, 0, 1, 3, 4)[case % 5]
         keep = case % 2
         engine.set_option(pem.OPT_STEP2_KERNEL, (1, 2, 0)[case % 3])

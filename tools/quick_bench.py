@@ -15,6 +15,7 @@ ap.add_argument("--small", action="store_true")
 ap.add_argument("--panels", type=int, default=1, help="multiply in this many sequential tile-row panels (results freed panel by panel)")
 ap.add_argument("--owner", type=int, default=0)
 ap.add_argument("--step1", type=int, default=0)
+ap.add_argument("--plans", type=int, default=1)
 ap.add_argument("--step2", type=int, default=0)
 ap.add_argument("--sweep", default="", help="comma list of owner:small_nnz:small_pairs variants timed on the same operands, e.g. 0:8:64,0:4:64,2:8:64")
 a = ap.parse_args()
@@ -23,6 +24,7 @@ ctx.set_option(pem.OPT_KEEP_EMPTY_TILES, a.keep_empty)
 ctx.set_option(pem.OPT_OWNER, a.owner)
 ctx.set_option(pem.OPT_STEP1_PATH, a.step1)
 ctx.set_option(pem.OPT_STEP2_KERNEL, a.step2)
+ctx.set_option(pem.OPT_SIZE_PLANS, a.plans)
 for k in a.configs:
     t0 = time.time()
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=a.small)

@@ -308,6 +308,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count
+    stalls0 = ctx.size_stalls
     step_ms, own_ms, s1, s2, s3, kms = [], [], [], [], [], []
     for _ in range(args.steps):
         barrier()
@@ -327,6 +328,7 @@ def main():
         s1.append(t.step1_ms); s2.append(t.step2_ms); s3.append(t.step3_ms)
         kms.append(kd)
     launches = ctx.launch_count - launches0
+    stalls = ctx.size_stalls - stalls0
     clocks = sampler.stop() if rank == 0 else None
     c_nnz, c_tiles, c_pairs = (int(x) for x in sizes.tolist())
     ms_per_step = float(np.mean(step_ms))
@@ -422,7 +424,10 @@ def main():
                                      "k_row_sort (step 1: block-local bitonic sort of each C' row's tile pairs)" if sort_passes == 0 else
                                      f"cub::DeviceRadixSort onesweep, {sort_passes} passes (step 1: sort of the kept tile pairs)"),
                       "k_step2_pairs": "k_step2_pairs (step 2: 16x16 boolean products, pair-parallel)",
-                      "step3_numeric": "k_step3_entries (step 3: fp64 numeric accumulation)"}[dom]
+                      "step3_numeric": {4: "k_step3_windows (step 3: fp64 numeric accumulation, pair records staged in shared memory)",
+                                        3: "k_step3_classes (step 3: fp64 numeric accumulation, tile classes)",
+                                        1: "k_step3_numeric (step 3: fp64 numeric accumulation, row-owner)"}.get(
+                                            ctx.last_step3_kernel, "k_step3_entries (step 3: fp64 numeric accumulation)")}[dom]
         td = kern_t[dom]
         # compulsory bytes of each timed kernel, whole job; the numeric kernel's are the
         # algorithmic bytes of the product (it reads A and B and writes C)
@@ -460,6 +465,7 @@ def main():
                     "what": "host COO (pinned) -> pem_convert_coo (values upload overlapped with the symbolic steps) -> pem_spgemm -> checksum/sizes read back"
                             + ("; every rank uploads 1/N of the COO and the slices are all-gathered over NVLink" if world > 1 else "")},
             "gpu_launches": int(launches),
+            "host_stalls_in_timed_steps": int(stalls),     # size read-backs that stalled the host (0: the warm-up steps recorded the size plans)
             "clocks": clocks,
         }
         if e2e_coo is not None:

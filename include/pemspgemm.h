@@ -152,6 +152,9 @@ int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n);
 /* How step 1 of the last product ordered its tile pairs: -1 = no sort (per-row bitmap path), 0 = block-local
  * sort of every C' row in shared memory, n > 0 = n passes of the global radix sort (labels the KT slot [1]). */
 int pem_ctx_last_sort_passes(const pem_ctx* ctx);
+/* Which numeric kernel step 3 of the last product ran (PEM_OPT_OWNER 0 chooses): 1 = row-owner, 2 = entry-owner,
+ * 3 = tile-class, 4 = window kernel (labels the KT slot [3] of pem_ctx_kernel_ms). */
+int pem_ctx_last_step3_kernel(const pem_ctx* ctx);
 /* Host stalls at device-size read-backs inside products since creation (diagnostic: five per first product of an
  * operand pair, none for its repeats under PEM_OPT_SIZE_PLANS; every product ends with one synchronisation). */
 int64_t pem_ctx_size_stalls(const pem_ctx* ctx);

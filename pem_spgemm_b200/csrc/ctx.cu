@@ -207,6 +207,8 @@ int pem_ctx_kernel_ms(const pem_ctx* ctx, double* ms, int n)
     return KT_N;
 }
 
+int pem_ctx_last_step3_kernel(const pem_ctx* ctx) { return ctx ? ctx->last_step3_kernel : 0; }
+
 int64_t pem_ctx_size_stalls(const pem_ctx* ctx) { return ctx ? ctx->size_stalls : 0; }
 
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx) { return ctx ? ctx->pool_mallocs : 0; }

@@ -41,6 +41,7 @@ struct pem_ctx {
     cudaMemPool_t pool = nullptr;
     std::string err;
     int64_t launches = 0;        // kernels of this library launched on the stream
+    int last_step3_kernel = 0;   // step 3 of the last product: 1 = row-owner, 2 = entry-owner, 3 = tile-class, 4 = window kernel
     int last_sort_passes = -1;   // step 1 of the last product: -1 = no sort (bitmap path), 0 = block-local row sort, n = n radix passes
     int opt_keep_empty = 0;      // PEM_OPT_KEEP_EMPTY_TILES
     int opt_step1_path = 0;      // PEM_OPT_STEP1_PATH

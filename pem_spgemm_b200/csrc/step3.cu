@@ -614,6 +614,7 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
         k_block_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->tile_nnz_ptr, C->blk_tile);
         PEM_LAUNCHED();
     }
+    ctx->last_step3_kernel = windows ? 4 : !by_records ? 1 : C->s3_entries ? 2 : 3;
     if (C->nnz > 0 && windows) {
         PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 160, 6>(ctx, A, B, C))
                                     : (launch_windows<double, 128, 160, 6>(ctx, A, B, C)));

@@ -42,10 +42,11 @@ for k in a.configs:
         for r in range(a.reps):
             t = pem.Times()
             C = ctx.spgemm(A, B, times=t)
+            cs = C.checksum()
             C.free()
             if bt is None or t.step3_ms < bt.step3_ms:
                 bt = t; bk = ctx.kernel_ms()
-        print(f"   sweep owner {ow} small_nnz {se} small_pairs {sp}: step1 {bt.step1_ms:.3f} step2 {bt.step2_ms:.3f} step3 {bt.step3_ms:.3f} total {bt.total_ms:.3f} | numeric kernel {bk['step3_numeric']:.3f}", flush=True)
+        print(f"   sweep owner {ow} small_nnz {se} small_pairs {sp}: step1 {bt.step1_ms:.3f} step2 {bt.step2_ms:.3f} step3 {bt.step3_ms:.3f} total {bt.total_ms:.3f} | numeric kernel {bk['step3_numeric']:.3f} | checksum {cs[0].hex()} {cs[1].hex()}", flush=True)
     ctx.set_option(pem.OPT_OWNER, a.owner); ctx.set_option(pem.OPT_S3_SMALL_NNZ, 8); ctx.set_option(pem.OPT_S3_SMALL_PAIRS, 64)
     for r in range(a.reps):
         t = pem.Times()

@@ -338,40 +338,162 @@ k_max_segment(int nrows, const int* __restrict__ off, int64_t* __restrict__ scal
     if ((threadIdx.x & 31) == 0 && len > 0) atomicMax((long long*)&scalars[SC_MAXD], (long long)len);
 }
 
-// One block per C' row: the row's (tile column, position) words are sorted by a
-// bitonic network in shared memory - position in the low bits makes the words distinct, so the order of
-// equal tile columns is the expansion order (ascending A tile), as a stable sort would give - and the
-// pairs are written out through the sorted positions.  One pass over the data where the radix sort
-// needs one per digit; for banded / stencil matrices (a few hundred pairs per row).
+// One block per C' row.  The row's pairs become (tile column, position) words in shared memory - position in the
+// low bits makes the words distinct, so the order of equal tile columns is the expansion order (ascending A tile),
+// as a stable sort would give.  Rows whose window of tile columns fits a small bitmap (stencil / FEM products: a
+// few hundred pairs over a few thousand columns) are ordered WITHOUT a comparison network: bitmap of the occupied
+// columns -> popcount prefix = rank of every column = the pair's group (its C' tile), counting scatter into the
+// groups, then each group (a tile's handful of pairs) is put in position order by one thread.  Seven block
+// barriers where the bitonic network needs one per stage (36 for 256 pairs); rows with a wide window or a long
+// group fall back to the network.  One pass over the data either way, where the radix sort needs one per digit.
+constexpr int RS_BMW = 256;            // bitmap words of the counting path: windows of up to 8192 tile columns
+constexpr int RS_GROUP_MAX = 32;       // longest group one thread sorts by insertion
+
+template <int THREADS>
+__device__ __forceinline__ unsigned rs_block_scan(unsigned* a, int n, unsigned* wsum)   // in-place exclusive scan, returns the total
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + THREADS - 1) / THREADS;
+    const int b = min(tid * per, n), e = min(b + per, n);
+    unsigned local = 0;
+    for (int i = b; i < e; ++i) local += a[i];
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const unsigned x = wsum[w];
+        if (w < warp) woff += x;
+        total += x;
+    }
+    unsigned run = woff + incl - local;
+    for (int i = b; i < e; ++i) {
+        const unsigned x = a[i];
+        a[i] = run;
+        run += x;
+    }
+    __syncthreads();
+    return total;
+}
+
 template <class KeyT, int THREADS, int POS_BITS>
 __global__ void __launch_bounds__(THREADS)
-k_row_sort(int wbits, const int* __restrict__ off, const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
+k_row_sort(int wbits, int CAP, const int* __restrict__ off, const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
            KeyT* __restrict__ out_key, int2* __restrict__ out_val)
 {
-    extern __shared__ unsigned sk[];
+    // CAP: power of two >= the longest row of this product (<= 1 << POS_BITS) and >= RS_BMW: sizes the arrays below
+    extern __shared__ unsigned sk[];                     // [CAP] the row's words
+    unsigned* ow = sk + CAP;                             // [CAP] words in group order
+    unsigned* cnt = ow + CAP;                            // [CAP] pairs per group -> group starts -> group ends
+    unsigned* bm = cnt + CAP;                            // [RS_BMW] occupied tile columns, then their popcount prefix
+    unsigned short* sg = reinterpret_cast<unsigned short*>(bm + RS_BMW);     // [CAP] group of every pair
+    __shared__ unsigned wsum[THREADS / 32];
+    __shared__ unsigned s_maxcol, s_maxgroup;
     const int r = blockIdx.x, tid = threadIdx.x;
     const int s = off[r], n = off[r + 1] - s;
     if (n == 0) return;                                  // uniform over the block
-    int N = 2;
-    while (N < n) N <<= 1;
     const KeyT jmask = ((KeyT)1 << wbits) - 1;
-    for (int i = tid; i < N; i += THREADS)
-        sk[i] = i < n ? ((unsigned)(in_key[s + i] & jmask) << POS_BITS) | (unsigned)i : 0xFFFFFFFFu;
+    if (tid == 0) { s_maxcol = 0; s_maxgroup = 0; }
+    for (int i = tid; i < RS_BMW; i += THREADS) bm[i] = 0;
     __syncthreads();
-    for (int k = 2; k <= N; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (N >> 1); t += THREADS) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // element with bit j clear
-                const int hi = lo | j;
-                const unsigned a = sk[lo], b = sk[hi];
-                const bool up = (lo & k) == 0;
-                if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+    unsigned mc = 0;
+    for (int i = tid; i < n; i += THREADS) {
+        const unsigned col = (unsigned)(in_key[s + i] & jmask);
+        sk[i] = (col << POS_BITS) | (unsigned)i;
+        mc = max(mc, col);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    if ((tid & 31) == 0) atomicMax(&s_maxcol, mc);
+    __syncthreads();
+    const unsigned* src = sk;                            // where the ordered words end up
+    bool counted = s_maxcol < (unsigned)RS_BMW * 32u;
+    if (counted) {
+        for (int i = tid; i < n; i += THREADS) {
+            const unsigned col = sk[i] >> POS_BITS;
+            atomicOr(&bm[col >> 5], 1u << (col & 31));
+        }
+        __syncthreads();
+        // bm[w] := (columns below word w) << 6 | nothing lost: keep the word itself in registers while scanning counts
+        unsigned words[(RS_BMW + THREADS - 1) / THREADS];
+#pragma unroll
+        for (int q = 0; q < (RS_BMW + THREADS - 1) / THREADS; ++q) {
+            const int w = tid + q * THREADS;
+            words[q] = w < RS_BMW ? bm[w] : 0u;
+            if (w < RS_BMW) cnt[w] = __popc(words[q]);
+        }
+        __syncthreads();
+        const int D = (int)rs_block_scan<THREADS>(cnt, RS_BMW, wsum);       // cnt[w] = distinct columns below word w
+        unsigned pre[(RS_BMW + THREADS - 1) / THREADS];
+#pragma unroll
+        for (int q = 0; q < (RS_BMW + THREADS - 1) / THREADS; ++q) {
+            const int w = tid + q * THREADS;
+            pre[q] = w < RS_BMW ? cnt[w] : 0u;
+        }
+        __syncthreads();
+        // the prefix moves behind the bitmap's role: ow is free until the scatter, so park it there
+#pragma unroll
+        for (int q = 0; q < (RS_BMW + THREADS - 1) / THREADS; ++q) {
+            const int w = tid + q * THREADS;
+            if (w < RS_BMW) ow[w] = pre[q];
+        }
+        for (int g = tid; g < D; g += THREADS) cnt[g] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) {
+            const unsigned col = sk[i] >> POS_BITS;
+            const unsigned g = ow[col >> 5] + __popc(bm[col >> 5] & ((1u << (col & 31)) - 1u));
+            sg[i] = (unsigned short)g;
+            atomicAdd(&cnt[g], 1u);
+        }
+        __syncthreads();
+        unsigned mg = 0;
+        for (int g = tid; g < D; g += THREADS) mg = max(mg, cnt[g]);
+        if (mg) atomicMax(&s_maxgroup, mg);
+        __syncthreads();
+        counted = s_maxgroup <= (unsigned)RS_GROUP_MAX;
+        if (counted) {
+            rs_block_scan<THREADS>(cnt, D, wsum);                            // group starts
+            for (int i = tid; i < n; i += THREADS) ow[atomicAdd(&cnt[sg[i]], 1u)] = sk[i];   // cnt[g] ends as the group's end
+            __syncthreads();
+            for (int g = tid; g < D; g += THREADS) {                         // position order inside the group
+                const int b = g ? (int)cnt[g - 1] : 0, e = (int)cnt[g];
+                for (int i = b + 1; i < e; ++i) {
+                    const unsigned key = ow[i];
+                    int x = i - 1;
+                    while (x >= b && ow[x] > key) { ow[x + 1] = ow[x]; --x; }
+                    ow[x + 1] = key;
+                }
             }
             __syncthreads();
+            src = ow;
         }
+    }
+    if (!counted) {                                      // bitonic network over the words
+        int N = 2;
+        while (N < n) N <<= 1;
+        for (int i = n + tid; i < N; i += THREADS) sk[i] = 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = 2; k <= N; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (N >> 1); t += THREADS) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // element with bit j clear
+                    const int hi = lo | j;
+                    const unsigned a = sk[lo], b = sk[hi];
+                    const bool up = (lo & k) == 0;
+                    if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+                }
+                __syncthreads();
+            }
+    }
     const KeyT rowbits = (KeyT)(unsigned)r << wbits;
     for (int i = tid; i < n; i += THREADS) {
-        const unsigned e = sk[i];
+        const unsigned e = src[i];
         out_key[s + i] = rowbits | (KeyT)(e >> POS_BITS);
         out_val[s + i] = in_val[s + (int)(e & ((1u << POS_BITS) - 1u))];
     }
@@ -563,7 +685,12 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     ctx->last_sort_passes = by_rows ? 0 : (wbits + rbits + 7) / 8;
     if (by_rows) {
         KT_BEGIN(KT_SORT);
-        k_row_sort<KeyT, 128, RS_SMALL_BITS><<<nrows, 128, RS_SMALL * 4, ctx->stream>>>(wbits, seg_off, key_a, val_a, key_b, val_b);
+        int cap = RS_BMW;                               // shared memory by the longest row: short rows keep more blocks per SM
+        while (cap < longest_row) cap <<= 1;
+        if (cap <= 256)
+            k_row_sort<KeyT, 64, RS_SMALL_BITS><<<nrows, 64, (size_t)cap * 14 + RS_BMW * 4, ctx->stream>>>(wbits, cap, seg_off, key_a, val_a, key_b, val_b);
+        else
+            k_row_sort<KeyT, 128, RS_SMALL_BITS><<<nrows, 128, (size_t)cap * 14 + RS_BMW * 4, ctx->stream>>>(wbits, cap, seg_off, key_a, val_a, key_b, val_b);
         KT_END(KT_SORT);
         E_LAUNCHED();
         std::swap(key_a, key_b);

@@ -323,7 +323,6 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
 // per-pair payloads (a warp issues them one lane at a time, ~36 ns per copy, tools/ubench/bulk_rate.cu).
 // =========================================================================================
 constexpr int S3W_THREADS = 256;
-constexpr int S3W_ECAP = 2048;      // nonzeros decoded per pass
 
 // win_tile[w] = first tile whose pair list starts at or after pair w * np (w = 0 .. n_windows)
 __global__ void __launch_bounds__(256)
@@ -344,7 +343,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 // shared-memory layout of the window kernel
-template <int NP, int SCAP>
+template <int NP, int SCAP, int ECAP>
 struct S3WLayout {
     static constexpr int REC = 0;
     static constexpr int VOFF = REC + SCAP * 128;
@@ -352,10 +351,10 @@ struct S3WLayout {
     static constexpr int PP = MASK + NP * 32;
     static constexpr int NZ = PP + (NP + 4) * 4;
     static constexpr int CODE = NZ + (NP + 4) * 4;
-    static constexpr int BYTES = CODE + S3W_ECAP * 2;
+    static constexpr int BYTES = CODE + ECAP * 2;
 };
 
-template <class T, int NP, int SCAP, int MINB>   // window pairs, staged pairs (multiple of 32)
+template <class T, int NP, int SCAP, int ECAP, int MINB>   // window pairs, staged pairs (multiple of 16), nonzeros decoded per pass
 __global__ void __launch_bounds__(S3W_THREADS, MINB)
 k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict__ c_tile_nnz_ptr,
                 const uint4* __restrict__ Cmasks128, const int64_t* __restrict__ pair_ptr,
@@ -364,8 +363,8 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
                 const uint32_t* __restrict__ B_off, const T* __restrict__ B_vals_t, const uint4* __restrict__ B_col_rec4,
                 T* __restrict__ C_vals)
 {
-    static_assert(SCAP % 32 == 0 && SCAP >= NP && SCAP / 32 <= S3W_THREADS / 32 && NP <= 128, "window shape");
-    using L = S3WLayout<NP, SCAP>;
+    static_assert(SCAP % 16 == 0 && SCAP >= NP && (SCAP + 31) / 32 <= S3W_THREADS / 32 && NP <= 128, "window shape");
+    using L = S3WLayout<NP, SCAP, ECAP>;
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_raw + L::REC);     // pair j: A row records [32j .. 32j+15], B column records [32j+16 .. 32j+31]
     uint2* s_voff = reinterpret_cast<uint2*>(s_raw + L::VOFF);         // pair j: first value of the A tile, of the B tile
@@ -404,7 +403,7 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
     for (int x = tid; x < nt * 2; x += S3W_THREADS) reinterpret_cast<uint4*>(s_mask)[x] = Cmasks128[ta * 2 + x];
     __syncthreads();
     const int ne = s_nz[nt];
-    for (int e0 = 0; e0 < ne; e0 += S3W_ECAP) {
+    for (int e0 = 0; e0 < ne; e0 += ECAP) {
         // ---- 2. decode: lane = one mask word (rows 2w, 2w+1) of one tile ---------------------------------
         for (int it0 = warp * 32; it0 < nt * 8; it0 += S3W_THREADS) {
             const int it = it0 + lane;
@@ -422,7 +421,7 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
                 do {
                     const unsigned b = __ffs(word) - 1;
                     word &= word - 1;
-                    if ((unsigned)rank < (unsigned)S3W_ECAP) s_code[rank] = (uint16_t)(base + b);
+                    if ((unsigned)rank < (unsigned)ECAP) s_code[rank] = (uint16_t)(base + b);
                     ++rank;
                 } while (word);
             }
@@ -430,7 +429,7 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
         if (e0 == 0) asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
         // ---- 3. one thread per nonzero ------------------------------------------------------------------
-        const int e1 = min(ne, e0 + S3W_ECAP);
+        const int e1 = min(ne, e0 + ECAP);
         for (int i = e0 + tid; i < e1; i += S3W_THREADS) {
             const unsigned code = s_code[i - e0];
             const unsigned tl = code >> 8, r = (code >> 4) & 15u, c = code & 15u;
@@ -454,12 +453,12 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
             }
             C_vals[N0 + i] = acc;
         }
-        if (e0 + S3W_ECAP < ne) __syncthreads();
+        if (e0 + ECAP < ne) __syncthreads();
     }
 }
 
 // one window-kernel configuration: table kernel + numeric kernel
-template <class T, int NP, int SCAP, int MINB>
+template <class T, int NP, int SCAP, int ECAP, int MINB>
 static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
 {
     const int64_t n_windows = (C->pairs + NP - 1) / NP;
@@ -468,8 +467,8 @@ static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, 
     PEM_TRY(pem_alloc(ctx, &win_tile, (size_t)n_windows + 1));
     k_window_tiles<<<pem_div_up(C->tiles + 1, 256), 256, 0, ctx->stream>>>(C->tiles, n_windows, NP, C->pair_ptr, win_tile);
     PEM_LAUNCHED();
-    auto kern = k_step3_windows<T, NP, SCAP, MINB>;
-    constexpr int smem = S3WLayout<NP, SCAP>::BYTES;
+    auto kern = k_step3_windows<T, NP, SCAP, ECAP, MINB>;
+    constexpr int smem = S3WLayout<NP, SCAP, ECAP>::BYTES;
     static bool attr_set = false;                               // opt in to > 48 KB of dynamic shared memory (once per process)
     if (!attr_set && smem > 48 * 1024) {
         PEM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -616,8 +615,11 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
     }
     ctx->last_step3_kernel = windows ? 4 : !by_records ? 1 : C->s3_entries ? 2 : 3;
     if (C->nnz > 0 && windows) {
-        PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 160, 6>(ctx, A, B, C))
-                                    : (launch_windows<double, 128, 160, 6>(ctx, A, B, C)));
+        // 128-pair windows, 144 staged pairs, 1024 nonzeros per decode pass: 26 KB of shared memory and 32 registers, so
+        // that eight blocks (64 warps) stay resident per SM: the kernel is bound by the latency of its value gathers, and
+        // 8 blocks measured 8.9 ms on config 4 against 10.3 ms with 6 (160 staged pairs, 2048 nonzeros per pass)
+        PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 144, 1024, 8>(ctx, A, B, C))
+                                    : (launch_windows<double, 128, 144, 1024, 8>(ctx, A, B, C)));
         C->stage = 3;
         return PEM_OK;
     }

@@ -83,8 +83,10 @@ typedef enum pem_option {
      *    (or any product / accessor that reads the values) has returned.  The symbolic steps 1 and 2 of a
      *    product read masks only, so they overlap the upload: on config 4 end to end 51 -> 45 ms. */
     PEM_OPT_ASYNC_VALUES = 6,
-    /* step-2 mask kernel: 0 (default) / 1 = one lane per (A tile, B tile) pair walking the shorter nonzero
-     * list; 2 = sixteen lanes per C' tile, row masks exchanged by shuffles (bit-identical; measured slower) */
+    /* step-2 mask kernel: one lane per (A tile, B tile) pair, 1 = walking the shorter nonzero list, 3 = from the
+     * two tiles' row masks alone (128-bit mask loads, product rows in registers), 0 (default) = 3 when A's tiles
+     * hold at least eight nonzeros on average, else 1; 2 = sixteen lanes per C' tile, row masks exchanged by
+     * shuffles (bit-identical; measured slower) */
     PEM_OPT_STEP2_KERNEL = 7,
     /* diagnostics: 1 = host-side timeline of step 1 on stderr (where the host waits), 2 = also per-phase cycle
      * counters of the bitmap kernels */

@@ -172,7 +172,7 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
             if (ctx->cached_bytes > ctx->cache_limit) pem_cache_release(ctx);
             return PEM_OK;
         case PEM_OPT_STEP2_KERNEL:
-            if (value < 0 || value > 2) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP2_KERNEL must be 0..2");
+            if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_STEP2_KERNEL must be 0..3");
             ctx->opt_step2_kernel = (int)value;
             return PEM_OK;
         case PEM_OPT_ASYNC_VALUES: ctx->opt_async_vals = value != 0; return PEM_OK;

@@ -48,7 +48,7 @@ struct pem_ctx {
     int opt_owner = 0;           // PEM_OPT_OWNER: 0 = automatic (window or entry-owner), 2 = entry-owner, 1 = row-owner (registers), 3 = tile-class kernel, 4 = window kernel
     int opt_trace = 0;           // PEM_OPT_TRACE: host-side timeline of step 1 on stderr
     int opt_esc_variant = 0;     // PEM_OPT_ESC_VARIANT: bit 0 = count-then-write expansion, bit 1 = no block-local row sort
-    int opt_step2_kernel = 0;    // PEM_OPT_STEP2_KERNEL: 0 / 1 = lane per pair, 2 = sixteen lanes per C' tile
+    int opt_step2_kernel = 0;    // PEM_OPT_STEP2_KERNEL: 0 = lane per pair (list or row-mask form by tile density), 1 = list form, 3 = row-mask form, 2 = sixteen lanes per C' tile
     int opt_async_vals = 0;      // PEM_OPT_ASYNC_VALUES: pem_convert_coo returns while the values' upload is still in flight
     int opt_s3_small_e = 8;      // PEM_OPT_S3_SMALL_NNZ: step 3 handles a tile with at most this many nonzeros ...
     int opt_s3_small_np = 64;    // PEM_OPT_S3_SMALL_PAIRS: ... and at most this many pairs with one thread

@@ -132,17 +132,26 @@ k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t
 // The products of a tile's pairs are OR-reduced by a segmented warp scan (pairs of a tile are
 // consecutive lanes); a run that lies inside one warp is stored, a run cut by a warp boundary is
 // merged with atomicOr into the zero-initialised mask array.
+//
+// ROWS = true (dense tiles: stencil / FEM operands, chosen on the host from nnz(A) / tiles(A)): the same product
+// from the ROW MASKS alone.  The lane loads A's sixteen row masks and B's sixteen row masks with two 128-bit
+// loads each (one 32-byte sector per tile: no nonzero list, no value offsets, no 1- and 2-byte gathers), parks
+// B's rows in its own shared-memory column (conflict-free, read back only by the lane that wrote them) and
+// forms prod[rows 2w, 2w+1] in a REGISTER per A mask word: one shared-memory load per A nonzero, nothing else
+// touches the load/store unit (the list form was bound by it: 91 % of the L1 throughput on config 4).
+template <bool ROWS>
 __global__ void __launch_bounds__(S2P_THREADS, 2048 / S2P_THREADS)
 k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
               const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
               const uint32_t* __restrict__ A_off, const uint8_t* __restrict__ A_rc,
-              const uint16_t* __restrict__ A_masks_t,
+              const uint16_t* __restrict__ A_masks_t, const uint16_t* __restrict__ Amasks,
               const uint32_t* __restrict__ B_off, const uint8_t* __restrict__ B_rc,
               const uint16_t* __restrict__ Bmasks,
               uint32_t* __restrict__ Cmasks32, uint32_t* __restrict__ hit_t)
 {
     __shared__ int s_ptr[S2P_THREADS + 2];
-    __shared__ unsigned s_acc[8 * S2P_THREADS];     // word w of thread t at [w * THREADS + t]: conflict-free
+    // list form: word w of thread t at [w * THREADS + t]; row form: B's row k of thread t at [k * THREADS + t] (conflict-free)
+    __shared__ unsigned s_acc[(ROWS ? 16 : 8) * S2P_THREADS];
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t i0 = (int64_t)blockIdx.x * S2P_THREADS;
     const int64_t t_lo = blk_tile[blockIdx.x];
@@ -152,8 +161,10 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
         const int64_t rel = pair_ptr[t_lo + x] - i0;
         s_ptr[x] = (int)max((int64_t)-0x40000000, min(rel, (int64_t)0x40000000));
     }
+    if (!ROWS) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s_acc[w * S2P_THREADS + tid] = 0u;
+        for (int w = 0; w < 8; ++w) s_acc[w * S2P_THREADS + tid] = 0u;
+    }
     __syncthreads();
     const int64_t i = i0 + tid;
     const bool valid = i < n_pairs;
@@ -173,7 +184,38 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
     //                           an ordinary B tile costs 1-2 steps instead of up to 256)
     unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool by_b = false;
-    if (valid) {
+    if (ROWS) {
+        if (valid) {
+            const int2 ab = pairs[i];
+            const uint4* __restrict__ a4 = reinterpret_cast<const uint4*>(Amasks + (size_t)(unsigned)ab.x * 16u);
+            const uint4* __restrict__ b4 = reinterpret_cast<const uint4*>(Bmasks + (size_t)(unsigned)ab.y * 16u);
+            const uint4 ax = a4[0], ay = a4[1], bx = b4[0], by = b4[1];
+            const unsigned bw[8] = {bx.x, bx.y, bx.z, bx.w, by.x, by.y, by.z, by.w};
+            unsigned* my = s_acc + tid;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {               // B row k of this pair at my[k * THREADS]
+                my[(2 * w) * S2P_THREADS] = bw[w] & 0xFFFFu;
+                my[(2 * w + 1) * S2P_THREADS] = bw[w] >> 16;
+            }
+            const unsigned aw[8] = {ax.x, ax.y, ax.z, ax.w, ay.x, ay.y, ay.z, ay.w};
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {               // word w = rows 2w (low half), 2w + 1 (high half)
+                unsigned m = aw[w] & 0xFFFFu, p = 0, q = 0;
+                while (m) {                             // prod[2w] = OR over k in Arow[2w] of Brow[k]: eight instructions per nonzero
+                    const unsigned k = __ffs(m) - 1u;
+                    m &= m - 1u;
+                    p |= my[k * S2P_THREADS];
+                }
+                m = aw[w] >> 16;
+                while (m) {
+                    const unsigned k = __ffs(m) - 1u;
+                    m &= m - 1u;
+                    q |= my[k * S2P_THREADS];
+                }
+                acc[w] = p | (q << 16);
+            }
+        }
+    } else if (valid) {
         const int2 ab = pairs[i];
         const uint32_t a0 = A_off[ab.x], a1 = A_off[ab.x + 1];
         const uint32_t b0 = B_off[ab.y], b1 = B_off[ab.y + 1];
@@ -202,7 +244,7 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
             }
         }
     }
-    if (!by_b) {
+    if (!ROWS && !by_b) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) acc[w] = s_acc[w * S2P_THREADS + tid];
     }
@@ -398,10 +440,16 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
                 k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
                 PEM_LAUNCHED();
             }
+            // row form for dense tiles (at least eight nonzeros per A tile on average; config 4: 17.9), list form otherwise
+            // (hypersparse tiles: one or two list steps per pair; hub tiles walk the shorter of the two lists)
+            const bool rows_form = ctx->opt_step2_kernel == 3 ||
+                                   (ctx->opt_step2_kernel == 0 && A->nnz >= 8 * (int64_t)A->tiles);
             KT_BEGIN(KT_PAIRS);
-            k_step2_pairs<<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(
-                C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->tile_nnz_ptr, A->rc_idx, A->masks_t,
-                B->tile_nnz_ptr, B->rc_idx, B->masks, reinterpret_cast<uint32_t*>(C->masks), C->pair_hit);
+#define S2P_ARGS C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->tile_nnz_ptr, A->rc_idx, A->masks_t, A->masks, \
+                B->tile_nnz_ptr, B->rc_idx, B->masks, reinterpret_cast<uint32_t*>(C->masks), C->pair_hit
+            if (rows_form) k_step2_pairs<true><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
+            else k_step2_pairs<false><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
+#undef S2P_ARGS
             KT_END(KT_PAIRS);
             PEM_LAUNCHED();
             pem_free(ctx, blk);

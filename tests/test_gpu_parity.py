@@ -418,11 +418,11 @@ def test_owner_variants_are_bit_identical(engine, k, owner):
     C0.free(); C1.free(); A.free(); B.free()
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("keep_empty", [0, 1])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_step2_kernels_match_tile_oracle(engine, k, keep_empty, kernel):
-    """Both step-2 mask kernels (lane per pair; sixteen lanes per C' tile) against the numpy restatement of
+    """The step-2 mask kernels (lane per pair in list form and in row-mask form; sixteen lanes per C' tile) against the numpy restatement of
     compute_CMasksAndOffsets (spgemm.cu:499-550), and the values that step 3 derives from their hit blocks."""
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
     engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep_empty)
@@ -704,7 +704,7 @@ def test_fuzz_all_variants_against_oracle(engine):
         path = (1, 3, 4, 5)[case % 4]
         owner = (2, 0, 1, 3, 4)[case % 5]
         keep = case % 2
-        engine.set_option(pem.OPT_STEP2_KERNEL, (1, 2, 0)[case % 3])
+        engine.set_option(pem.OPT_STEP2_KERNEL, (1, 2, 0, 3)[case % 4])
         engine.set_option(pem.OPT_STEP1_PATH, path)
         engine.set_option(pem.OPT_OWNER, owner)
         engine.set_option(pem.OPT_KEEP_EMPTY_TILES, keep)

@@ -23,7 +23,8 @@
 //             non-empty.  Kept products are written in product order (ballot/popc ranks inside a
 //             warp, a block scan across warps) as key = (C' row, tile column - jmin(row)),
 //             value = (p, q).
-//   compact   blocks wrote at their product base; k_compact closes the holes.
+//   compact   inside k_expand: the chunks' kept counts are chained by decoupled look-back while the kernel runs,
+//             so every chunk writes straight to its final, compacted position (one pass over the pairs).
 //   sort      ONE stable LSD radix sort of (key, value) over exactly the key bits in use.  Products
 //             were emitted in ascending p, and p ascends with (row, k), so after a stable sort by
 //             (row, column) every C' tile's pairs are contiguous and already in ascending k: the
@@ -183,8 +184,38 @@ k_merge_split(int nchunks, int np, int64_t P, const int64_t* __restrict__ pptr, 
     split[b] = (int32_t)lo;
 }
 
-// MODE 0: count kept products per chunk.  MODE 1: also write them (at out_base[b], or at the chunk's
-// first product index when out_base is null).
+// Exclusive prefix of this chunk's count over all earlier chunks, found while the kernel runs (decoupled look-back):
+// every chunk publishes its own count (AGGREGATE), then walks back over its predecessors' words, 32 at a time,
+// summing aggregates until it meets one whose INCLUSIVE prefix is known, and publishes its own inclusive prefix.
+// Chunk ids are tickets drawn when a block starts, so every predecessor is already running: no block waits on a
+// block that has not been scheduled.  Flag and value share one 64-bit word (single store, no fence needed).
+__device__ __forceinline__ int64_t chain_prefix(unsigned long long* state, int b, int64_t mine, int lane)
+{
+    constexpr unsigned long long AGG = 1ull << 62, INC = 2ull << 62, VAL = (1ull << 62) - 1ull;
+    if (lane == 0) atomicExch(&state[b], (b == 0 ? INC : AGG) | (unsigned long long)mine);
+    if (b == 0) return 0;
+    int64_t prefix = 0;
+    for (int j = b - 1;; j -= 32) {
+        const int idx = j - lane;
+        unsigned long long sv;
+        do {
+            sv = idx >= 0 ? *reinterpret_cast<volatile unsigned long long*>(&state[idx]) : INC;
+        } while (__any_sync(0xffffffffu, (sv >> 62) == 0ull));
+        const unsigned inc = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
+        const int first = inc ? __ffs(inc) - 1 : 31;     // nearest predecessor with a known inclusive prefix
+        int64_t v = lane <= first ? (int64_t)(sv & VAL) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prefix += v;
+        if (inc) break;
+    }
+    if (lane == 0) atomicExch(&state[b], INC | (unsigned long long)(prefix + mine));
+    return prefix;
+}
+
+// MODE 0: count kept products per chunk.  MODE 1: also write them at out_base[b].  MODE 2: ONE pass: count, find the
+// chunk's output offset by look-back over the chunks' counts (chunk_cnt doubles as the look-back state, zeroed by the
+// caller; its last entry receives the total) and write the kept products compacted, in product order.
 // SLICED: the work items are (A tile, column) pairs over B's row slices (k_items) instead of A tiles
 // over B' rows; item_p / srow_tile translate item -> A tile and slice position -> B tile.
 template <class KeyT, int MODE, bool SLICED>
@@ -194,17 +225,25 @@ k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, co
          const int32_t* __restrict__ item_p, const int32_t* __restrict__ srow_tile,
          const int32_t* __restrict__ Arow, const int32_t* __restrict__ Bcol,
          const uint16_t* __restrict__ BrowOcc, const int* __restrict__ jmin, int wbits, int keep_empty,
-         const int64_t* __restrict__ out_base, int64_t* __restrict__ chunk_cnt,
+         const int64_t* __restrict__ out_base, int64_t* __restrict__ chunk_cnt, int* __restrict__ ticket,
          KeyT* __restrict__ out_key, int2* __restrict__ out_val)
 {
     __shared__ int s_rel[EX_CHUNK + 2];       // product offset of slice tile t, relative to the chunk's first product
     __shared__ unsigned s_q0[EX_CHUNK + 1];   // first B tile of tile t's B' row, minus s_rel[t] (mod 2^32)
     __shared__ unsigned short s_occ[EX_CHUNK + 1];
     __shared__ unsigned s_wcnt[EX_WARPS];
+    __shared__ int s_chunk;
+    __shared__ int64_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int chunk = blockIdx.x;
+    if (MODE == 2) {                          // chunks in the order the blocks start (see chain_prefix)
+        if (tid == 0) s_chunk = atomicAdd(ticket, 1);
+        __syncthreads();
+        chunk = s_chunk;
+    }
     const int64_t total = (int64_t)np + P;
-    const int64_t d0 = (int64_t)blockIdx.x * EX_CHUNK, d1 = min(d0 + EX_CHUNK, total);
-    const int i0 = split[blockIdx.x], i1 = split[blockIdx.x + 1];
+    const int64_t d0 = (int64_t)chunk * EX_CHUNK, d1 = min(d0 + EX_CHUNK, total);
+    const int i0 = split[chunk], i1 = split[chunk + 1];
     const int64_t j0 = d0 - i0, j1 = d1 - i1;           // products [j0, j1)
     const int nprod = (int)(j1 - j0);
     const int nt = min(i1 + 1, np) - i0;                // slice tiles [i0, i0 + nt)
@@ -275,9 +314,22 @@ k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, co
         before += w < warp ? c : 0u;
         all += c;
     }
-    if (tid == 0 && chunk_cnt) chunk_cnt[blockIdx.x] = all;
+    if (MODE != 2 && tid == 0 && chunk_cnt) chunk_cnt[chunk] = all;
     if (MODE == 0) return;
-    int64_t pos = (out_base ? out_base[blockIdx.x] : j0) + before;
+    int64_t pos;
+    if (MODE == 2) {
+        if (warp == 0) {
+            const int64_t prefix = chain_prefix(reinterpret_cast<unsigned long long*>(chunk_cnt), chunk, (int64_t)all, lane);
+            if (lane == 0) {
+                s_base = prefix;
+                if (chunk == (int)gridDim.x - 1) chunk_cnt[gridDim.x] = prefix + (int64_t)all;   // total kept pairs
+            }
+        }
+        __syncthreads();
+        pos = s_base + before;
+    } else {
+        pos = out_base[chunk] + before;
+    }
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int u = 0; u < EX_ITEMS; ++u) {
@@ -292,22 +344,6 @@ k_expand(int np, int p0, int rb, int64_t P, const int64_t* __restrict__ pptr, co
             out_val[at] = make_int2(p, qq[u]);
         }
         pos += __popc(bal);
-    }
-}
-
-// close the holes between the chunks' outputs (written at their product bases)
-template <class KeyT>
-__global__ void __launch_bounds__(256)
-k_compact(const int32_t* __restrict__ split, const int64_t* __restrict__ chunk_off,
-          const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
-          KeyT* __restrict__ out_key, int2* __restrict__ out_val)
-{
-    const int64_t src = (int64_t)blockIdx.x * EX_CHUNK - split[blockIdx.x];
-    const int64_t dst = chunk_off[blockIdx.x];
-    const int n = (int)(chunk_off[blockIdx.x + 1] - dst);
-    for (int i = threadIdx.x; i < n; i += 256) {
-        out_key[dst + i] = in_key[src + i];
-        out_val[dst + i] = in_val[src + i];
     }
 }
 
@@ -385,7 +421,7 @@ __device__ __forceinline__ unsigned rs_block_scan(unsigned* a, int n, unsigned* 
 template <class KeyT, int THREADS, int POS_BITS>
 __global__ void __launch_bounds__(THREADS)
 k_row_sort(int wbits, int CAP, const int* __restrict__ off, const KeyT* __restrict__ in_key, const int2* __restrict__ in_val,
-           KeyT* __restrict__ out_key, int2* __restrict__ out_val)
+           KeyT* __restrict__ out_key, int2* __restrict__ out_val, int64_t* __restrict__ row_tiles)
 {
     // CAP: power of two >= the longest row of this product (<= 1 << POS_BITS) and >= RS_BMW: sizes the arrays below
     extern __shared__ unsigned sk[];                     // [CAP] the row's words
@@ -394,12 +430,12 @@ k_row_sort(int wbits, int CAP, const int* __restrict__ off, const KeyT* __restri
     unsigned* bm = cnt + CAP;                            // [RS_BMW] occupied tile columns, then their popcount prefix
     unsigned short* sg = reinterpret_cast<unsigned short*>(bm + RS_BMW);     // [CAP] group of every pair
     __shared__ unsigned wsum[THREADS / 32];
-    __shared__ unsigned s_maxcol, s_maxgroup;
+    __shared__ unsigned s_maxcol, s_maxgroup, s_heads;
     const int r = blockIdx.x, tid = threadIdx.x;
     const int s = off[r], n = off[r + 1] - s;
     if (n == 0) return;                                  // uniform over the block
     const KeyT jmask = ((KeyT)1 << wbits) - 1;
-    if (tid == 0) { s_maxcol = 0; s_maxgroup = 0; }
+    if (tid == 0) { s_maxcol = 0; s_maxgroup = 0; s_heads = 0; }
     for (int i = tid; i < RS_BMW; i += THREADS) bm[i] = 0;
     __syncthreads();
     unsigned mc = 0;
@@ -472,6 +508,7 @@ k_row_sort(int wbits, int CAP, const int* __restrict__ off, const KeyT* __restri
             }
             __syncthreads();
             src = ow;
+            if (tid == 0) s_heads = (unsigned)D;         // the groups ARE the row's C' tiles
         }
     }
     if (!counted) {                                      // bitonic network over the words
@@ -492,10 +529,75 @@ k_row_sort(int wbits, int CAP, const int* __restrict__ off, const KeyT* __restri
             }
     }
     const KeyT rowbits = (KeyT)(unsigned)r << wbits;
-    for (int i = tid; i < n; i += THREADS) {
-        const unsigned e = src[i];
-        out_key[s + i] = rowbits | (KeyT)(e >> POS_BITS);
-        out_val[s + i] = in_val[s + (int)(e & ((1u << POS_BITS) - 1u))];
+    if (counted) {                                       // (uniform over the block)
+        for (int i = tid; i < n; i += THREADS) {
+            const unsigned e = src[i];
+            out_key[s + i] = rowbits | (KeyT)(e >> POS_BITS);
+            out_val[s + i] = in_val[s + (int)(e & ((1u << POS_BITS) - 1u))];
+        }
+    } else {                                             // the network does not know the runs of equal tile columns: count them
+        unsigned heads = 0;
+        for (int i = tid; i < n; i += THREADS) {
+            const unsigned e = src[i];
+            heads += (i == 0 || (src[i - 1] >> POS_BITS) != (e >> POS_BITS)) ? 1u : 0u;
+            out_key[s + i] = rowbits | (KeyT)(e >> POS_BITS);
+            out_val[s + i] = in_val[s + (int)(e & ((1u << POS_BITS) - 1u))];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) heads += __shfl_xor_sync(0xffffffffu, heads, o);
+        if ((tid & 31) == 0 && heads) atomicAdd(&s_heads, heads);
+        __syncthreads();
+    }
+    if (tid == 0) row_tiles[r] = (int64_t)s_heads;      // C' tiles of this row: scanned into C's row pointer by the caller
+}
+
+// C' tiles of the row-sorted pairs: one warp per C' row walks the row's sorted keys, numbers the runs of equal
+// tile columns from the row's first tile (row_ptr, the scan of k_row_sort's counts) and writes every tile's
+// (row, column, first pair), plus the first tile of every PEM_PAIR_BLOCK-pair block of step 2.  Replaces the
+// select of run heads over all pairs + k_ctiles on this path.
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+k_row_tiles(int nrows, int rb, int wbits, int64_t ntiles, int64_t npairs, const int* __restrict__ off,
+            const KeyT* __restrict__ keys, const int64_t* __restrict__ row_ptr, const int* __restrict__ jmin,
+            int64_t* __restrict__ pair_ptr, int32_t* __restrict__ tile_row, int32_t* __restrict__ tile_col,
+            int32_t* __restrict__ pair_blk)
+{
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    if (row == 0 && lane == 0) pair_ptr[ntiles] = npairs;
+    const int s = off[row], n = off[row + 1] - s;
+    if (n == 0) return;
+    const KeyT jmask = ((KeyT)1 << wbits) - 1;
+    const int64_t t0 = row_ptr[row];
+    const int j0 = jmin[row];
+    int running = 0;
+    constexpr int U = 8;                                 // 256 pairs per trip: eight independent key loads in flight per lane
+    KeyT last = 0;                                       // key of the pair before this trip's first
+    for (int base = 0; base < n; base += 32 * U) {
+        KeyT k[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * 32 + lane;
+            k[u] = i < n ? keys[s + i] : (KeyT)0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * 32 + lane;
+            const bool valid = i < n;
+            KeyT kp = __shfl_up_sync(0xffffffffu, k[u], 1);
+            if (lane == 0) kp = last;
+            last = __shfl_sync(0xffffffffu, k[u], 31);
+            const bool head = valid && (i == 0 || kp != k[u]);
+            const unsigned bal = __ballot_sync(0xffffffffu, head);
+            const int64_t t = t0 + running + __popc(bal & (0xffffffffu >> (31 - lane))) - 1;   // tile of pair s + i
+            if (head) {
+                pair_ptr[t] = s + i;
+                tile_row[t] = rb + row;
+                tile_col[t] = j0 + (int)(k[u] & jmask);
+            }
+            if (valid && ((s + i) & (PEM_PAIR_BLOCK - 1)) == 0) pair_blk[(s + i) / PEM_PAIR_BLOCK] = (int32_t)t;
+            running += __popc(bal);
+        }
     }
 }
 constexpr int RS_SMALL = 1024, RS_SMALL_BITS = 10;
@@ -582,8 +684,8 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
     k_merge_split<<<pem_div_up((int64_t)nchunks + 1, 256), 256, 0, ctx->stream>>>(nchunks, np, P, pptr, split);
     E_LAUNCHED();
 
-    // Staged layout (one expansion): chunks write at their product base into P-sized buffers, then
-    // the holes are closed.  When P-sized buffers would be too large, count first and write exactly.
+    // One expansion into P-sized buffers (the kept count F <= P is not known on the host yet), compacted on the fly.
+    // When P-sized buffers would be too large, count first, read F back and write exactly.
     // free device memory, from the context's own books (cudaMemGetInfo takes ~0.7 ms on a B200 box)
     const size_t free_b = ctx->free_at_create > ctx->pool_taken ? ctx->free_at_create - ctx->pool_taken : 0;
     const size_t staged_bytes = (size_t)P * (sizeof(KeyT) + sizeof(int2));
@@ -596,32 +698,35 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         pem_free(ctx, val_b);
         staged = false;
     }
+    if (staged && (pem_alloc(ctx, &key_a, (size_t)P) != PEM_OK || pem_alloc(ctx, &val_a, (size_t)P) != PEM_OK)) {
+        pem_free(ctx, key_a); pem_free(ctx, val_a); pem_free(ctx, key_b); pem_free(ctx, val_b);
+        staged = false;
+    }
+    int* ticket = reinterpret_cast<int*>(ctx->d_scalars + SC_T0);      // zeroed with the other scalars at the start of step 1
     if (staged) {
+        // one pass: the chunks' counts are chained by look-back while the kernel runs, the kept pairs land compacted
+        E_CK(cudaMemsetAsync(chunk_off, 0, ((size_t)nchunks + 1) * 8, ctx->stream));
+        E_CK(cudaMemsetAsync(ticket, 0, 4, ctx->stream));
         KT_BEGIN(KT_EXPAND);
-        k_expand<KeyT, 1, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
+        k_expand<KeyT, 2, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
             np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
-            B->row_occ, jmin, wbits, ctx->opt_keep_empty, nullptr, chunk_off, key_b, val_b);
+            B->row_occ, jmin, wbits, ctx->opt_keep_empty, nullptr, chunk_off, ticket, key_a, val_a);
         KT_END(KT_EXPAND);
         E_LAUNCHED();
     } else {
         k_expand<KeyT, 0, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
             np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
-            B->row_occ, jmin, wbits, ctx->opt_keep_empty, nullptr, chunk_off, nullptr, nullptr);
+            B->row_occ, jmin, wbits, ctx->opt_keep_empty, nullptr, chunk_off, nullptr, nullptr, nullptr);
         E_LAUNCHED();
+        E_CK(cudaMemsetAsync(chunk_off + nchunks, 0, 8, ctx->stream));
+        E_TRY(pem_scan_exclusive_i64(ctx, chunk_off, (int64_t)nchunks + 1));
     }
-    E_CK(cudaMemsetAsync(chunk_off + nchunks, 0, 8, ctx->stream));
-    E_TRY(pem_scan_exclusive_i64(ctx, chunk_off, (int64_t)nchunks + 1));
     const int64_t* d_F = chunk_off + nchunks;              // kept pairs, on the device
     // Short rows (banded / stencil matrices) are sorted row by row in shared memory: one pass over the
     // pairs.  Power-law inputs have rows of millions of pairs and keep the global radix sort.  Whether every
     // row is short is decided from the longest row, which travels to the host together with F: one stall.
     const bool consider_rows = P < 0x7fffffffLL && wbits + RS_SMALL_BITS <= 32 && !(ctx->opt_esc_variant & 2);
     if (staged) {
-        // compaction target and sort buffer sized by the products (F <= P is not known on the host yet)
-        E_TRY(pem_alloc(ctx, &key_a, (size_t)P));
-        E_TRY(pem_alloc(ctx, &val_a, (size_t)P));
-        k_compact<KeyT><<<nchunks, 256, 0, ctx->stream>>>(split, chunk_off, key_b, val_b, key_a, val_a);
-        E_LAUNCHED();
         E_CK(cudaMemsetAsync(ctx->d_scalars + SC_MAXD, 0, 8, ctx->stream));
         if (consider_rows) {
             E_TRY(pem_alloc(ctx, &seg_off, (size_t)nrows + 1));
@@ -661,7 +766,7 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         E_TRY(pem_alloc(ctx, &val_a, (size_t)F));
         k_expand<KeyT, 1, SLICED><<<nchunks, EX_THREADS, 0, ctx->stream>>>(
             np, p0, rb, P, pptr, split, bfirst, item_mask, item_p, B->srow_tile, A->tile_row_idx, B->tile_col_idx,
-            B->row_occ, jmin, wbits, ctx->opt_keep_empty, chunk_off, nullptr, key_a, val_a);
+            B->row_occ, jmin, wbits, ctx->opt_keep_empty, chunk_off, nullptr, nullptr, key_a, val_a);
         E_LAUNCHED();
         E_TRY(pem_alloc(ctx, &key_b, (size_t)F));
         E_TRY(pem_alloc(ctx, &val_b, (size_t)F));
@@ -688,13 +793,43 @@ int esc_run(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C,
         int cap = RS_BMW;                               // shared memory by the longest row: short rows keep more blocks per SM
         while (cap < longest_row) cap <<= 1;
         if (cap <= 256)
-            k_row_sort<KeyT, 64, RS_SMALL_BITS><<<nrows, 64, (size_t)cap * 14 + RS_BMW * 4, ctx->stream>>>(wbits, cap, seg_off, key_a, val_a, key_b, val_b);
+            k_row_sort<KeyT, 64, RS_SMALL_BITS><<<nrows, 64, (size_t)cap * 14 + RS_BMW * 4, ctx->stream>>>(wbits, cap, seg_off, key_a, val_a, key_b, val_b, C->row_ptr);
         else
-            k_row_sort<KeyT, 128, RS_SMALL_BITS><<<nrows, 128, (size_t)cap * 14 + RS_BMW * 4, ctx->stream>>>(wbits, cap, seg_off, key_a, val_a, key_b, val_b);
+            k_row_sort<KeyT, 128, RS_SMALL_BITS><<<nrows, 128, (size_t)cap * 14 + RS_BMW * 4, ctx->stream>>>(wbits, cap, seg_off, key_a, val_a, key_b, val_b, C->row_ptr);
         KT_END(KT_SORT);
         E_LAUNCHED();
         std::swap(key_a, key_b);
         std::swap(val_a, val_b);
+        pem_free(ctx, key_b);
+        pem_free(ctx, val_b);
+        // the sort counted every row's C' tiles: their scan is C's row pointer, its last entry the tile count
+        E_TRY(pem_scan_exclusive_i64(ctx, C->row_ptr, (int64_t)nrows + 1));
+        int64_t T = 0;
+        {
+            pem_size_read rd(ctx);
+            E_TRY(rd.add(C->row_ptr + nrows, 1));
+            E_TRY(rd.get(&T));
+        }
+        if (T >= 0x7fffffffLL) {
+            cleanup();
+            return ctx->fail(PEM_ERR_LIMIT, "more than 2^31 C' tiles in one result: multiply in tile-row panels (pem_spgemm_panel)");
+        }
+        tr.mark("row sort done, T known");
+        C->tiles = T;
+        pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col); pem_free(ctx, C->pair_ptr);
+        E_TRY(pem_alloc(ctx, &C->tile_row, (size_t)T));
+        E_TRY(pem_alloc(ctx, &C->tile_col, (size_t)T));
+        E_TRY(pem_alloc(ctx, &C->pair_ptr, (size_t)T + 1));
+        pem_free(ctx, C->pair_blk);
+        E_TRY(pem_alloc(ctx, &C->pair_blk, (size_t)((F + PEM_PAIR_BLOCK - 1) / PEM_PAIR_BLOCK) + 1));
+        k_row_tiles<KeyT><<<pem_div_up((int64_t)nrows * 32, 256), 256, 0, ctx->stream>>>(
+            nrows, rb, wbits, T, F, seg_off, key_a, C->row_ptr, jmin, C->pair_ptr, C->tile_row, C->tile_col, C->pair_blk);
+        E_LAUNCHED();
+        C->pair_list = val_a;
+        val_a = nullptr;
+        cleanup();
+        tr.mark("esc_run end (k_row_tiles launched)");
+        return PEM_OK;
     } else {   // stable radix sort by (row, column) over the bits in use
         cub::DoubleBuffer<KeyT> dk(key_a, key_b);
         cub::DoubleBuffer<unsigned long long> dv((unsigned long long*)val_a, (unsigned long long*)val_b);

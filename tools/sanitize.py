@@ -13,8 +13,8 @@ for k in (1, 2, 3, 4):
         I, J, V = I[keep], J[keep], V[keep]
     A = ctx.convert_coo(rows, cols, I, J, V)
     B = ctx.convert_coo(rows, cols, I, J, V, transpose=True) if tb else A
-    for path in (1, 3, 4):
-        for owner, step2 in ((2, 1), (3, 2), (1, 0)):
+    for path in (1, 3, 4, 5):
+        for owner, step2 in ((2, 1), (3, 2), (1, 0), (4, 3), (0, 0)):
             ctx.set_option(pem.OPT_STEP1_PATH, path); ctx.set_option(pem.OPT_OWNER, owner); ctx.set_option(pem.OPT_STEP2_KERNEL, step2)
             C = ctx.spgemm(A, B)
             s = C.checksum(); r, c, v = C.to_coo(); rp, cc, vv = C.to_csr(); C.free()

@@ -93,10 +93,11 @@ k_tile_products(int p0, int np, int rb, const int32_t* __restrict__ Acol, const 
             items = __popc(occ);
             icnt[i] = (int64_t)items;
             const int64_t* sp = srow_ptr + (size_t)k * 16;
-            while (occ) {
+            while (occ) {                       // per RUN of occupied columns: slices of consecutive rows are consecutive
                 const int c = __ffs(occ) - 1;
-                occ &= occ - 1;
-                cost += (unsigned long long)(sp[c + 1] - sp[c]);
+                const int len = __ffs(~(occ >> c)) - 1;
+                occ &= ~(((1u << len) - 1u) << c);
+                cost += (unsigned long long)(sp[c + len] - sp[c]);
             }
         }
     } else if (i == np) {

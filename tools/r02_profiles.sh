@@ -3,7 +3,7 @@
 # the second SpGEMM iteration, exported to text on the box (the .ncu-rep files are too large to travel back).
 cd "$(dirname "$0")/.."
 tag=${1:-r2p}
-RX='k_step3_entries|k_step2_pairs|k_expand|Onesweep|k_row_sort|k_step1_count|k_step1_fill|k_build_tiles|k_ctiles'
+RX='k_step3_entries|k_step3_windows|k_step2_pairs|k_expand|Onesweep|k_row_sort|k_row_tiles|k_tile_products|k_step1_count|k_step1_fill|k_build_tiles|k_ctiles'
 full() {   # config, launch-skip, count, extra quick_bench flags
   local k=$1 skip=$2 cnt=$3; shift 3
   timeout 1200 ncu --set full --clock-control none -k regex:"$RX" --launch-skip $skip -c $cnt -f -o gpurun_out/full_${tag}_c$k \
@@ -15,9 +15,11 @@ full() {   # config, launch-skip, count, extra quick_bench flags
 }
 for k in 1 2 3 4; do bash tools/launch_list.sh $tag $k; done
 QB_FLAGS="--panels 16 --reps 1" bash tools/launch_list.sh $tag 5
-full 1 5 4 --reps 2          # bitmap step 1: build_tiles once, then count, fill, pairs, entries
-full 2 9 8 --reps 2          # radix path: build_tiles, then expand, 4 x onesweep, ctiles, pairs, entries
-full 3 9 8 --reps 2
-full 4 6 5 --reps 2          # row sort: build_tiles, then expand, row_sort, ctiles, pairs, entries
-full 5 9 8 --panels 16 --reps 1     # second panel of the first product
+# kernels matched per product: bitmap path 4 (count, fill, pairs, numeric); radix path 9 (tile_products, expand, 4 x onesweep,
+# ctiles, pairs, entries); row-sort path 6 (tile_products, expand, row_sort, row_tiles, pairs, windows); + k_build_tiles per conversion
+full 1 5 4 --reps 2
+full 2 10 9 --reps 2
+full 3 11 9 --reps 2
+full 4 7 6 --reps 2
+full 5 10 9 --panels 16 --reps 1     # second panel of the first product
 du -sh gpurun_out

@@ -104,7 +104,18 @@ typedef enum pem_option {
      * remembered values while every kernel still computes the sizes on the device, which are compared after the
      * product's single final synchronisation (on a mismatch the product is redone with the stalls).  0: every product
      * stalls at its read-backs (five per product).  Setting the option clears the remembered sizes. */
-    PEM_OPT_SIZE_PLANS = 11
+    PEM_OPT_SIZE_PLANS = 11,
+    /* 1 (default): a repeated product whose sizes are remembered (PEM_OPT_SIZE_PLANS) is captured as ONE CUDA graph
+     * the second time it runs and launched as such from then on: its ~20-40 kernels, memsets and size copies cost one
+     * launch, which is what bounds small operands (config 1: 15 kernels for 0.15 ms of device time) and the short
+     * per-GPU panels of a multi-GPU run.  The graph owns the device blocks its product touches, result included: a
+     * result handed out from it borrows them, and the graph runs again only after that result was freed (a product
+     * called while the previous result is alive takes the ordinary path).  A product with a host stall inside, or
+     * whose blocks would take the graphs' memory past PEM_OPT_GRAPH_LIMIT_MB, silently stays on the ordinary path.
+     * Freeing an operand drops its plans and graphs.  0: no graphs. */
+    PEM_OPT_GRAPHS = 12,
+    /* budget for the device memory held by product graphs, MiB (default: a quarter of the memory free at pem_ctx_create) */
+    PEM_OPT_GRAPH_LIMIT_MB = 13
 } pem_option;
 
 /* Milliseconds.  Device times are CUDA-event times on the context's stream; wall times are
@@ -160,6 +171,8 @@ int pem_ctx_last_step3_kernel(const pem_ctx* ctx);
 /* Host stalls at device-size read-backs inside products since creation (diagnostic: five per first product of an
  * operand pair, none for its repeats under PEM_OPT_SIZE_PLANS; every product ends with one synchronisation). */
 int64_t pem_ctx_size_stalls(const pem_ctx* ctx);
+/* Products that ran as a single graph launch since creation (PEM_OPT_GRAPHS; diagnostic). */
+int64_t pem_ctx_graph_replays(const pem_ctx* ctx);
 /* Allocations that missed the context's block cache and went to the CUDA pool since creation
  * (diagnostic: a steady-state loop should not add any). */
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx);

@@ -34,6 +34,8 @@ OPT_TRACE = 8
 OPT_ESC_VARIANT = 9
 OPT_CACHE_LIMIT_MB = 10
 OPT_SIZE_PLANS = 11
+OPT_GRAPHS = 12
+OPT_GRAPH_LIMIT_MB = 13
 
 # pem_tiled_array / pem_result_array -> (index, dtype)
 T_ARRAYS = {
@@ -77,7 +79,7 @@ class ResultInfo(C.Structure):
 
 EXPORTS = [
     "pem_ctx_create", "pem_ctx_destroy", "pem_last_error", "pem_ctx_set_option", "pem_ctx_stream",
-    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_size_stalls", "pem_ctx_last_step3_kernel", "pem_ctx_pool_bytes", "pem_ctx_trim", "pem_convert_coo", "pem_convert_coo_f32", "pem_tiled_dtype", "pem_result_dtype", "pem_convert_csr", "pem_tiled_transpose",
+    "pem_ctx_sync", "pem_ctx_launch_count", "pem_ctx_last_sort_passes", "pem_ctx_kernel_ms", "pem_ctx_pool_mallocs", "pem_ctx_size_stalls", "pem_ctx_graph_replays", "pem_ctx_last_step3_kernel", "pem_ctx_pool_bytes", "pem_ctx_trim", "pem_convert_coo", "pem_convert_coo_f32", "pem_tiled_dtype", "pem_result_dtype", "pem_convert_csr", "pem_tiled_transpose",
     "pem_tiled_info_get", "pem_tiled_values_ready",
     "pem_tiled_free", "pem_tiled_get", "pem_tiled_device_ptr", "pem_count_flop", "pem_partition_panels",
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
@@ -118,6 +120,7 @@ def load():
         "pem_ctx_trim": (C.c_int, [vp]),
         "pem_ctx_pool_mallocs": (i64, [vp]),
         "pem_ctx_size_stalls": (i64, [vp]),
+        "pem_ctx_graph_replays": (i64, [vp]),
         "pem_ctx_last_step3_kernel": (C.c_int, [vp]),
         "pem_ctx_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
         "pem_convert_coo": (C.c_int, [vp, i32, i32, i64, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Times)]),
@@ -232,6 +235,11 @@ class Context:
     def size_stalls(self) -> int:
         """Host stalls at device-size read-backs inside products since the context was created."""
         return int(load().pem_ctx_size_stalls(self._h))
+
+    @property
+    def graph_replays(self) -> int:
+        """Products that ran as one CUDA-graph launch since the context was created (OPT_GRAPHS)."""
+        return int(load().pem_ctx_graph_replays(self._h))
 
     def trim(self):
         """Hand the cached device blocks back to the driver."""

@@ -700,6 +700,8 @@ int pem_tiled_build_srow(pem_ctx* ctx, const pem_tiled* Bc)
 {
     pem_tiled* B = const_cast<pem_tiled*>(Bc);
     if (B->srow_ptr) return PEM_OK;
+    // a handle's caches outlive any product: never built from a graph's arena (the capture is given up instead)
+    if (ctx->cap) return ctx->fail(PEM_ERR_CUDA, "operand cache built inside a graph capture");
     const size_t rows16 = (size_t)B->tile_rows * 16;
     int64_t* ptr = nullptr;
     PEM_TRY(pem_alloc(ctx, &ptr, rows16 + 1));
@@ -734,6 +736,8 @@ int pem_tiled_build_views(pem_ctx* ctx, const pem_tiled* Tc, bool as_a, bool as_
 {
     pem_tiled* T = const_cast<pem_tiled*>(Tc);
     const size_t n16 = (size_t)T->tiles * 16;
+    if (ctx->cap && ((as_a && !T->row_rec) || (as_b && !T->col_rec)))
+        return ctx->fail(PEM_ERR_CUDA, "operand cache built inside a graph capture");
     if (as_a && !T->row_rec) {
         uint32_t* rec = nullptr;
         PEM_TRY(pem_alloc(ctx, &rec, n16));

@@ -19,9 +19,49 @@
 // only handed back to the driver when an allocation fails, when the cache outgrows its limit (80 % of the
 // memory that was free when the context was created; PEM_OPT_CACHE_LIMIT_MB) or on pem_ctx_trim:
 // unmapping and re-mapping tens of GB costs seconds, far more than any kernel here.
+//
+// While a product is being captured into a CUDA graph (ctx->cap, pem_spgemm_panel) every block it takes joins
+// the graph's arena and stays there: freed blocks go to the arena's own idle list (later allocations of the same
+// capture reuse them: the graph is one chain, so stream order holds), never back to the shared cache, because
+// the graph bakes their addresses in.  A miss goes to the pool on the COPY stream (the engine's stream is
+// capturing); pem_spgemm_panel drains that stream before the first launch of the graph.
+static int graph_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
+{
+    pem_graph& g = *ctx->cap;
+    auto own = [&](void* q, size_t sz) {
+        g.arena.emplace_back(q, sz);
+        g.owned.insert(q);
+        g.bytes += sz;
+    };
+    auto it = g.idle.lower_bound(bytes);
+    if (it != g.idle.end() && it->first - bytes <= it->first / 4) {
+        *p = it->second;
+        g.idle.erase(it);
+        return PEM_OK;
+    }
+    it = ctx->free_blocks.lower_bound(bytes);
+    if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 4) {
+        *p = it->second;
+        ctx->live_blocks[*p] = it->first;
+        ctx->cached_bytes -= it->first;
+        own(*p, it->first);
+        ctx->free_blocks.erase(it);
+        return PEM_OK;
+    }
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->copy_stream);
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMallocFromPoolAsync (graph arena)", __FILE__, __LINE__);
+    g.side_allocs = true;
+    ctx->live_blocks[*p] = bytes;
+    ctx->pool_taken += bytes;
+    ++ctx->pool_mallocs;
+    own(*p, bytes);
+    return PEM_OK;
+}
+
 int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
 {
     bytes = (bytes + 511) & ~(size_t)511;
+    if (ctx->cap) return graph_alloc_bytes(ctx, p, bytes);
     auto it = ctx->free_blocks.lower_bound(bytes);
     if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 4) {
         *p = it->second;
@@ -46,6 +86,10 @@ int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
 
 void pem_free_bytes(pem_ctx* ctx, void* p)
 {
+    if (ctx->cap && ctx->cap->owned.count(p)) {     // stays in the arena (and in live_blocks)
+        ctx->cap->idle.emplace(ctx->live_blocks[p], p);
+        return;
+    }
     auto it = ctx->live_blocks.find(p);
     if (it == ctx->live_blocks.end()) {     // not ours (should not happen): plain stream-ordered free
         cudaFreeAsync(p, ctx->stream);
@@ -54,6 +98,21 @@ void pem_free_bytes(pem_ctx* ctx, void* p)
     ctx->free_blocks.emplace(it->second, p);
     ctx->cached_bytes += it->second;
     ctx->live_blocks.erase(it);
+}
+
+// a graph hands its arena back to the shared cache when the last holder (its plan, or a result borrowed from it) lets go
+pem_graph::~pem_graph()
+{
+    if (exec) cudaGraphExecDestroy(exec);
+    if (!ctx) return;
+    for (auto& b : arena)
+        if (ctx->live_blocks.count(b.first)) pem_free_bytes(ctx, b.first);
+    ctx->graph_bytes -= std::min(ctx->graph_bytes, bytes);
+}
+
+void pem_graph_opts(const pem_ctx* ctx, int* o)
+{
+    o[0] = ctx->opt_owner; o[1] = ctx->opt_step2_kernel; o[2] = ctx->opt_s3_small_e; o[3] = ctx->opt_s3_small_np; o[4] = ctx->opt_trace;
 }
 
 void pem_cache_release(pem_ctx* ctx)
@@ -113,6 +172,7 @@ int pem_ctx_create(pem_ctx** out, int device)
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         ctx->cache_limit = free_b / 5 * 4;      // of what was FREE at creation: other allocators in the process keep theirs
+        ctx->graph_limit = free_b / 4;
         ctx->free_at_create = free_b;
     }
     *out = ctx;
@@ -124,6 +184,7 @@ void pem_ctx_destroy(pem_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->plans.clear();                      // idle product graphs hand their arenas back to the cache
     pem_cache_release(ctx);
     for (auto& kv : ctx->live_blocks) cudaFreeAsync(kv.first, ctx->stream);   // handles the caller leaked
     cudaStreamSynchronize(ctx->stream);
@@ -161,6 +222,14 @@ int pem_ctx_set_option(pem_ctx* ctx, int option, int64_t value)
         case PEM_OPT_SIZE_PLANS:
             ctx->opt_plans = value != 0;
             ctx->plans.clear();
+            return PEM_OK;
+        case PEM_OPT_GRAPHS:
+            ctx->opt_graphs = value != 0;
+            for (auto& kv : ctx->plans) { kv.second.graph.reset(); kv.second.graph_failed = false; }
+            return PEM_OK;
+        case PEM_OPT_GRAPH_LIMIT_MB:
+            if (value < 0) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_GRAPH_LIMIT_MB must be >= 0");
+            ctx->graph_limit = (size_t)value << 20;
             return PEM_OK;
         case PEM_OPT_ESC_VARIANT:
             if (value < 0 || value > 3) return ctx->fail(PEM_ERR_ARG, "PEM_OPT_ESC_VARIANT must be 0..3");
@@ -212,6 +281,8 @@ int pem_ctx_last_step3_kernel(const pem_ctx* ctx) { return ctx ? ctx->last_step3
 int64_t pem_ctx_size_stalls(const pem_ctx* ctx) { return ctx ? ctx->size_stalls : 0; }
 
 int64_t pem_ctx_pool_mallocs(const pem_ctx* ctx) { return ctx ? ctx->pool_mallocs : 0; }
+
+int64_t pem_ctx_graph_replays(const pem_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 
 int pem_ctx_trim(pem_ctx* ctx)
 {
@@ -294,6 +365,10 @@ void pem_tiled_free(pem_ctx* ctx, pem_tiled* t)
     if (!ctx || !t) return;
     (void)pem_tiled_wait_vals(ctx, t);       // a gather still in flight on the copy stream writes t->vals
     if (t->ev_vals) cudaEventDestroy(t->ev_vals);
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end();) {    // size plans and product graphs of this operand
+        if ((uint64_t)it->first[0] == t->uid || (uint64_t)it->first[1] == t->uid) it = ctx->plans.erase(it);
+        else ++it;
+    }
     pem_free(ctx, t->vals); pem_free(ctx, t->tile_nnz_ptr); pem_free(ctx, t->masks);
     pem_free(ctx, t->masks_t); pem_free(ctx, t->row_ptr); pem_free(ctx, t->tile_row_ptr);
     pem_free(ctx, t->tile_col_idx); pem_free(ctx, t->tile_row_idx); pem_free(ctx, t->col_occ);
@@ -357,6 +432,16 @@ int pem_result_get(pem_ctx* ctx, const pem_result* C, int which, void* host_dst,
 void pem_result_free(pem_ctx* ctx, pem_result* C)
 {
     if (!ctx || !C) return;
+    if (C->graph) {
+        // buffers borrowed from a product graph stay in its arena (the graph may run again now); anything added to
+        // the result later (Ctiles_rowColIdx on demand) was allocated the ordinary way
+        void** fields[] = {(void**)&C->row_ptr, (void**)&C->tile_row, (void**)&C->tile_col, (void**)&C->pair_ptr,
+                           (void**)&C->pair_list, (void**)&C->pair_hit, (void**)&C->blk_tile, (void**)&C->pair_blk,
+                           (void**)&C->masks, (void**)&C->tile_nnz_ptr, (void**)&C->row_col_idx, (void**)&C->vals};
+        for (void** f : fields)
+            if (*f && C->graph->owned.count(*f)) *f = nullptr;
+        C->graph->busy = false;
+    }
     pem_free(ctx, C->row_ptr); pem_free(ctx, C->tile_row); pem_free(ctx, C->tile_col);
     pem_free(ctx, C->pair_ptr); pem_free(ctx, C->pair_list); pem_free(ctx, C->pair_hit); pem_free(ctx, C->blk_tile); pem_free(ctx, C->pair_blk);
     pem_free(ctx, C->masks); pem_free(ctx, C->tile_nnz_ptr); pem_free(ctx, C->row_col_idx);

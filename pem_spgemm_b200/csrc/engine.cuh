@@ -7,8 +7,10 @@
 #include <cstdio>
 #include <atomic>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "pemspgemm.h"
@@ -22,10 +24,14 @@ enum { PEM_NSCALARS = 24, PEM_NEVENTS = 8, PEM_PLAN_MAX = 96 };
 // A repeated product of the same operands replays them instead of stalling the host at every read-back: the
 // kernels still compute every size on the device, the copies are only compared after the product's final sync
 // (a mismatch cannot happen for immutable handles; if it does, the product is redone with the stalls).
+struct pem_graph;
 struct pem_plan {
     int64_t v[PEM_PLAN_MAX];
     int n = 0;
     bool valid = false;
+    // PEM_OPT_GRAPHS: the replayed product captured as one CUDA graph over buffers the graph owns (spgemm.cu)
+    std::shared_ptr<pem_graph> graph;
+    bool graph_failed = false;      // the capture was tried and given up (a host stall inside, or over the memory budget)
 };
 // pairs per block of step 2's pair kernel; step 1 (k_ctiles) emits the first tile of every such block
 constexpr int PEM_PAIR_BLOCK = 128;
@@ -61,6 +67,10 @@ struct pem_ctx {
     bool plan_replay = false;
     int plan_pos = 0;
     int opt_plans = 1;            // PEM_OPT_SIZE_PLANS
+    int opt_graphs = 1;           // PEM_OPT_GRAPHS: repeats of a product run as one captured CUDA graph
+    pem_graph* cap = nullptr;     // graph being captured: allocations come from / go back to its arena
+    size_t graph_bytes = 0, graph_limit = (size_t)8 << 30;   // bytes held by graph arenas / their budget (a quarter of the memory free at creation)
+    int64_t graph_replays = 0;    // products that ran as a graph launch since creation (pem_ctx_graph_replays)
     int64_t size_stalls = 0;      // host stalls at size read-backs since creation (pem_ctx_size_stalls)
     int64_t* d_scalars = nullptr; // device mirror the kernels reduce into
     cudaEvent_t ev[PEM_NEVENTS] = {};
@@ -108,8 +118,13 @@ struct PemRange {
         if (e__ != cudaSuccess) return ctx->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
     } while (0)
 
-#define KT_BEGIN(id) do { cudaEventRecord(ctx->kev[2 * (id)], ctx->stream); } while (0)
-#define KT_END(id) do { cudaEventRecord(ctx->kev[2 * (id) + 1], ctx->stream); ctx->kt_seen[id] = true; } while (0)
+// timing events: inside a graph capture they become event-record nodes that record on every launch of the graph
+static inline cudaError_t pem_event_record(pem_ctx* ctx, cudaEvent_t ev)
+{
+    return cudaEventRecordWithFlags(ev, ctx->stream, ctx->cap ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+#define KT_BEGIN(id) do { pem_event_record(ctx, ctx->kev[2 * (id)]); } while (0)
+#define KT_END(id) do { pem_event_record(ctx, ctx->kev[2 * (id) + 1]); ctx->kt_seen[id] = true; } while (0)
 
 #define PEM_TRY(expr)                    \
     do {                                 \
@@ -210,8 +225,29 @@ struct pem_result {
     int32_t* blk_tile = nullptr;      // entry-owner variant: first tile of each 128-entry step-3 block
     int32_t* pair_blk = nullptr;      // first tile of each 256-pair step-2 block (optional by-product of step 1)
     double* vals = nullptr;           // [nnz]
+    std::shared_ptr<pem_graph> graph; // set when the buffers above belong to a product graph's arena (pem_result_free hands them back to it)
 };
 
+// A repeated product captured as ONE CUDA graph (PEM_OPT_GRAPHS; pem_spgemm_panel).  The graph bakes device
+// pointers in, so it owns every block its product touches (the arena: result buffers and temporaries): a result
+// handed out from it borrows the result buffers, and the graph can run again once that result has been freed.
+struct pem_graph {
+    pem_ctx* ctx = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<std::pair<void*, size_t>> arena;   // every block taken during the capture
+    std::unordered_set<void*> owned;               // the same pointers, for pem_result_free
+    std::multimap<size_t, void*> idle;             // arena blocks free at the current point of the capture
+    size_t bytes = 0;
+    bool busy = false;                // a result borrowed from this graph is alive
+    bool side_allocs = false;         // blocks came from the pool on the copy stream during the capture
+    pem_result tmpl;                  // the product's result as the captured run left it
+    int64_t launches = 0;             // kernels per launch of the graph
+    int last_step3_kernel = 0, last_sort_passes = -1;
+    bool kt_seen[KT_N] = {};
+    int opts[5] = {};                 // options the kernel choice depends on (owner, step-2 kernel, small-tile limits, trace)
+    ~pem_graph();
+};
+void pem_graph_opts(const pem_ctx* ctx, int* o);
 
 // scalars slots in ctx->d_scalars / h_scalars
 enum {

@@ -10,6 +10,8 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include <climits>
+#include <memory>
+#include <unordered_set>
 #include <chrono>
 #include <algorithm>
 
@@ -493,6 +495,30 @@ int pem_result_make_rowcolidx(pem_ctx* ctx, pem_result* C)
     return PEM_OK;
 }
 
+// a result whose buffers went back to the allocator behind its back (abandoned graph capture): drop the pointers
+static void result_forget_buffers(pem_result* C)
+{
+    C->row_ptr = nullptr; C->tile_row = nullptr; C->tile_col = nullptr; C->pair_ptr = nullptr; C->pair_list = nullptr;
+    C->pair_hit = nullptr; C->blk_tile = nullptr; C->pair_blk = nullptr; C->masks = nullptr; C->tile_nnz_ptr = nullptr;
+    C->row_col_idx = nullptr; C->vals = nullptr;
+}
+
+// hand every block of an abandoned (or over-budget) graph arena back to ordinary ownership: `keep` are the
+// pointers a live result still uses (they stay live blocks of the context), the rest goes to the cache
+static void graph_dissolve(pem_ctx* ctx, pem_graph* g, const pem_result* keep)
+{
+    std::unordered_set<const void*> held;
+    if (keep) {
+        const void* f[] = {keep->row_ptr, keep->tile_row, keep->tile_col, keep->pair_ptr, keep->pair_list, keep->pair_hit,
+                           keep->blk_tile, keep->pair_blk, keep->masks, keep->tile_nnz_ptr, keep->row_col_idx, keep->vals};
+        for (const void* q : f) if (q) held.insert(q);
+    }
+    for (auto& b : g->arena)
+        if (!held.count(b.first) && ctx->live_blocks.count(b.first)) pem_free_bytes(ctx, b.first);
+    g->arena.clear(); g->owned.clear(); g->idle.clear(); g->bytes = 0;
+    if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+}
+
 int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
                      int32_t rb, int32_t re, pem_result** out, pem_times* times)
 {
@@ -508,34 +534,124 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
     // synchronisation) by every later one
     const std::vector<int64_t> key = {(int64_t)A->uid, (int64_t)B->uid, rb, re, ctx->opt_keep_empty, ctx->opt_step1_path,
                                       ctx->opt_esc_variant};
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // the three steps, enqueued on the context's stream (or captured from it)
+    auto run_steps = [&]() -> int {
+        PEM_CK(pem_event_record(ctx, ctx->ev[2]));
+        int rc = pem_step1_symbolic(ctx, A, B, rb, re, &C);
+        pem_event_record(ctx, ctx->ev[3]);
+        if (rc == PEM_OK) rc = pem_step2_symbolic(ctx, A, B, C);
+        pem_event_record(ctx, ctx->ev[4]);
+        if (rc == PEM_OK) rc = pem_step3_numeric(ctx, A, B, C);
+        pem_event_record(ctx, ctx->ev[5]);
+        return rc;
+    };
+    int redo = 0;
+    for (;;) {
         ctx->plan = nullptr;
         ctx->plan_replay = false;
         ctx->plan_pos = 0;
+        pem_plan* plan = nullptr;
         if (ctx->opt_plans) {
             if (ctx->plans.size() > 256) ctx->plans.clear();
-            pem_plan& pl = ctx->plans[key];
-            ctx->plan = &pl;
-            ctx->plan_replay = pl.valid;
+            plan = &ctx->plans[key];
+            ctx->plan = plan;
+            ctx->plan_replay = plan->valid;
         }
         for (int i = 0; i < KT_N; ++i) { ctx->kt_seen[i] = false; ctx->kt_ms[i] = 0.0; }
-        PEM_CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-        int rc = pem_step1_symbolic(ctx, A, B, rb, re, &C);
-        cudaEventRecord(ctx->ev[3], ctx->stream);
-        if (rc == PEM_OK) rc = pem_step2_symbolic(ctx, A, B, C);
-        cudaEventRecord(ctx->ev[4], ctx->stream);
-        if (rc == PEM_OK) rc = pem_step3_numeric(ctx, A, B, C);
-        cudaEventRecord(ctx->ev[5], ctx->stream);
-        if (rc == PEM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-            rc = ctx->fail_cuda(cudaGetLastError(), "cudaStreamSynchronize after step 3", __FILE__, __LINE__);
+        // Product graph (PEM_OPT_GRAPHS): the second product of a plan is CAPTURED from the stream while the host code
+        // below replays the plan (so it never stalls), then launched; later products launch the same graph.
+        int gopts[5];
+        pem_graph_opts(ctx, gopts);
+        const bool graph_ok = plan && plan->valid && ctx->opt_graphs && !plan->graph_failed && !ctx->opt_trace &&
+                              !A->vals_pending && !B->vals_pending;
+        std::shared_ptr<pem_graph> g;
+        bool launch_only = false, capture = false;
+        if (graph_ok && plan->graph) {
+            launch_only = !plan->graph->busy && std::equal(gopts, gopts + 5, plan->graph->opts);
+            if (launch_only) g = plan->graph;
+        } else if (graph_ok) {
+            g = std::make_shared<pem_graph>();
+            std::copy(gopts, gopts + 5, g->opts);
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                capture = true;
+                ctx->cap = g.get();
+            } else {
+                (void)cudaGetLastError();
+                plan->graph_failed = true;
+                g.reset();
+            }
+        }
+        int rc = PEM_OK;
+        if (launch_only) {
+            cudaError_t e = cudaGraphLaunch(g->exec, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = ctx->fail_cuda(e, "launch of a product graph", __FILE__, __LINE__);
+            else {
+                C = new pem_result(g->tmpl);
+                C->graph = g;
+                g->busy = true;
+                ctx->launches += g->launches;
+                ctx->last_step3_kernel = g->last_step3_kernel;
+                ctx->last_sort_passes = g->last_sort_passes;
+                for (int i = 0; i < KT_N; ++i) ctx->kt_seen[i] = g->kt_seen[i];
+                ctx->plan_pos = plan->n;
+                ++ctx->graph_replays;
+            }
+        } else if (capture) {
+            const int64_t launches0 = ctx->launches;
+            rc = run_steps();
+            ctx->cap = nullptr;
+            cudaGraph_t gr = nullptr;
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &gr);
+            if (rc == PEM_OK && e == cudaSuccess && gr) e = cudaGraphInstantiate(&g->exec, gr, 0);
+            if (gr) cudaGraphDestroy(gr);
+            if (rc == PEM_OK && e == cudaSuccess && g->exec && g->side_allocs) e = cudaStreamSynchronize(ctx->copy_stream);
+            if (rc == PEM_OK && e == cudaSuccess && g->exec) e = cudaGraphLaunch(g->exec, ctx->stream);
+            if (rc == PEM_OK && e == cudaSuccess && g->exec) e = cudaStreamSynchronize(ctx->stream);
+            if (rc != PEM_OK || e != cudaSuccess || !g->exec) {
+                // not capturable (a host stall or an unsupported call inside), or the launch failed: give the blocks
+                // back, remember not to try again, and run this product the ordinary way
+                (void)cudaGetLastError();
+                (void)cudaStreamSynchronize(ctx->stream);
+                (void)cudaGetLastError();
+                graph_dissolve(ctx, g.get(), nullptr);
+                if (C) { result_forget_buffers(C); delete C; C = nullptr; }
+                plan->graph_failed = true;
+                ctx->err.clear();
+                ctx->plan = nullptr;
+                ctx->plan_replay = false;
+                continue;
+            }
+            g->ctx = ctx;
+            g->launches = ctx->launches - launches0;
+            g->last_step3_kernel = ctx->last_step3_kernel;
+            g->last_sort_passes = ctx->last_sort_passes;
+            for (int i = 0; i < KT_N; ++i) g->kt_seen[i] = ctx->kt_seen[i];
+            ++ctx->graph_replays;
+            if (ctx->graph_bytes + g->bytes <= ctx->graph_limit) {
+                g->tmpl = *C;
+                C->graph = g;
+                g->busy = true;
+                plan->graph = g;
+                ctx->graph_bytes += g->bytes;
+            } else {                                    // over the budget: this product keeps its buffers as an ordinary result
+                g->ctx = nullptr;
+                graph_dissolve(ctx, g.get(), C);
+                plan->graph_failed = true;
+            }
+        } else {
+            rc = run_steps();
+            if (rc == PEM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                rc = ctx->fail_cuda(cudaGetLastError(), "cudaStreamSynchronize after step 3", __FILE__, __LINE__);
+        }
         pem_plan* pl = ctx->plan;
         const bool replayed = ctx->plan_replay;
         const int npos = ctx->plan_pos;
         ctx->plan = nullptr;
         ctx->plan_replay = false;
         if (rc != PEM_OK) {
-            if (pl) ctx->plans.erase(key);
             pem_result_free(ctx, C);
+            if (pl) ctx->plans.erase(key);
             return rc;
         }
         if (!pl) break;
@@ -547,10 +663,10 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
         bool same = npos == pl->n;
         for (int i = 0; same && i < npos; ++i) same = ctx->h_check[i] == pl->v[i];
         if (same) break;
-        ctx->plans.erase(key);                      // never expected: redo the product with the stalls
-        pem_result_free(ctx, C);
+        pem_result_free(ctx, C);                    // never expected: redo the product with the stalls
         C = nullptr;
-        if (attempt == 1) return ctx->fail(PEM_ERR_CUDA, "sizes changed under a replayed size plan");
+        ctx->plans.erase(key);
+        if (++redo == 2) return ctx->fail(PEM_ERR_CUDA, "sizes changed under a replayed size plan");
     }
     auto w1 = std::chrono::high_resolution_clock::now();
     for (int i = 0; i < KT_N; ++i) {
@@ -560,9 +676,9 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
     }
     if (times) {
         float s1 = 0, s2 = 0, s3 = 0;
-        cudaEventElapsedTime(&s1, ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&s2, ctx->ev[3], ctx->ev[4]);
-        cudaEventElapsedTime(&s3, ctx->ev[4], ctx->ev[5]);
+        if (cudaEventElapsedTime(&s1, ctx->ev[2], ctx->ev[3]) != cudaSuccess) { s1 = 0; (void)cudaGetLastError(); }
+        if (cudaEventElapsedTime(&s2, ctx->ev[3], ctx->ev[4]) != cudaSuccess) { s2 = 0; (void)cudaGetLastError(); }
+        if (cudaEventElapsedTime(&s3, ctx->ev[4], ctx->ev[5]) != cudaSuccess) { s3 = 0; (void)cudaGetLastError(); }
         times->step1_ms = s1; times->step2_ms = s2; times->step3_ms = s3;
         times->kernel_ms = (double)s1 + s2 + s3;
         times->total_ms = std::chrono::duration<double, std::milli>(w1 - w0).count();

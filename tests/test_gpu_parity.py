@@ -395,6 +395,114 @@ def test_size_plans_replay_without_stalls(engine, k, step1_path):
         B.free()
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("step1_path", [0, 1, 2])
+def test_product_graphs_replay_bit_identical(engine, k, step1_path):
+    """PEM_OPT_GRAPHS: the second product of an operand pair is captured as one CUDA graph, later ones are single graph
+    launches over the graph's own buffers.  Same bits as the ordinary path; a product called while the previous result
+    is alive takes the ordinary path; results of panels, option changes and operand frees keep working."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    engine.set_option(pem.OPT_STEP1_PATH, step1_path)
+    engine.set_option(pem.OPT_SIZE_PLANS, 1)
+    engine.set_option(pem.OPT_GRAPHS, 1)
+    try:
+        C = engine.spgemm(A, B)                       # records the sizes
+        ref = C.checksum()
+        C.free()
+        g0 = engine.graph_replays
+        l0 = engine.launch_count
+        C = engine.spgemm(A, B)                       # captured + launched
+        assert engine.graph_replays == g0 + 1, "the second product of a plan should have been captured as a graph"
+        per_product = engine.launch_count - l0
+        assert per_product > 0
+        _assert_same_C(C, oC)
+        C.free()
+        for _ in range(3):                            # graph launches
+            s1, g1, l1 = engine.size_stalls, engine.graph_replays, engine.launch_count
+            t = pem.Times()
+            C = engine.spgemm(A, B, times=t)
+            assert engine.graph_replays == g1 + 1 and engine.size_stalls == s1
+            assert engine.launch_count - l1 == per_product
+            assert C.checksum() == ref
+            assert t.step1_ms > 0 and t.step3_ms >= 0 and t.kernel_ms > 0      # the timing events live inside the graph
+            _assert_same_C(C, oC)
+            C.free()
+        # previous result alive: the graph's buffers are lent out, so this product runs the ordinary way
+        C1 = engine.spgemm(A, B)
+        g1 = engine.graph_replays
+        C2 = engine.spgemm(A, B)
+        assert engine.graph_replays == g1
+        _assert_same_C(C1, oC); _assert_same_C(C2, oC)
+        assert C1.array("row_col_idx").size == oC.nnz           # an array added to a graph-backed result later on
+        C1.free(); C2.free()
+        C = engine.spgemm(A, B)                       # lent buffers are back: a graph launch again
+        assert engine.graph_replays == g1 + 1
+        _assert_same_C(C, oC)
+        C.free()
+        # panels have their own plans and graphs
+        bounds = engine.partition_panels(A, B, 2)
+        for rep in range(3):
+            g1 = engine.graph_replays
+            parts = [engine.spgemm(A, B, panel=(int(bounds[i]), int(bounds[i + 1]))) for i in range(2)]
+            assert engine.graph_replays - g1 == (0 if rep == 0 else 2)
+            assert sum(p.info.nnz for p in parts) == oC.nnz
+            coo = [p_.to_coo() for p_ in parts]
+            ro, co, vo = oC.to_coo()
+            for j, want in enumerate((ro, co, vo)):
+                assert np.array_equal(np.concatenate([x[j] for x in coo]), want)
+            for p_ in parts:
+                p_.free()
+        # another kernel choice is not what the graph holds: ordinary path, same bits
+        engine.set_option(pem.OPT_OWNER, 2)
+        g1 = engine.graph_replays
+        C = engine.spgemm(A, B)
+        assert engine.graph_replays == g1
+        _assert_same_C(C, oC)
+        C.free()
+        engine.set_option(pem.OPT_OWNER, 0)
+        # a budget of zero: the capture runs once, its product stays an ordinary result, no graph is kept
+        engine.set_option(pem.OPT_GRAPHS, 1)          # drops the graphs
+        engine.set_option(pem.OPT_GRAPH_LIMIT_MB, 0)
+        for rep in range(3):
+            g1 = engine.graph_replays
+            C = engine.spgemm(A, B)
+            assert engine.graph_replays - g1 == (1 if rep == 0 else 0)
+            _assert_same_C(C, oC)
+            C.free()
+        engine.set_option(pem.OPT_GRAPH_LIMIT_MB, 16384)
+        engine.set_option(pem.OPT_GRAPHS, 0)
+        g1 = engine.graph_replays
+        C = engine.spgemm(A, B)
+        assert engine.graph_replays == g1
+        _assert_same_C(C, oC)
+        C.free()
+        # freeing an operand drops its graphs; the buffers are reusable by whatever comes next
+        engine.set_option(pem.OPT_GRAPHS, 1)
+        for _ in range(3):
+            C = engine.spgemm(A, B); C.free()
+        C = engine.spgemm(A, B)                       # graph-backed and alive while the operands go away
+    finally:
+        engine.set_option(pem.OPT_GRAPHS, 1)
+        engine.set_option(pem.OPT_GRAPH_LIMIT_MB, 16384)
+        engine.set_option(pem.OPT_OWNER, 0)
+        engine.set_option(pem.OPT_STEP1_PATH, 0)
+    if B is not A:
+        B.free()
+    A.free()
+    _assert_same_C(C, oC)                             # the result outlives its graph's plan
+    C.free()
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+    for _ in range(3):
+        C = engine.spgemm(A, B)
+        _assert_same_C(C, oC)
+        C.free()
+    B.free(); A.free()
+
+
 @pytest.mark.parametrize("owner", [1, 2, 3, 4])
 @pytest.mark.parametrize("k", [1, 2, 3, 4])
 def test_owner_variants_are_bit_identical(engine, k, owner):

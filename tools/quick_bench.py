@@ -17,6 +17,7 @@ ap.add_argument("--owner", type=int, default=0)
 ap.add_argument("--step1", type=int, default=0)
 ap.add_argument("--plans", type=int, default=1)
 ap.add_argument("--step2", type=int, default=0)
+ap.add_argument("--graphs", type=int, default=1)
 ap.add_argument("--sweep", default="", help="comma list of owner:small_nnz:small_pairs variants timed on the same operands, e.g. 0:8:64,0:4:64,2:8:64")
 a = ap.parse_args()
 ctx = pem.Context(0)
@@ -25,6 +26,7 @@ ctx.set_option(pem.OPT_OWNER, a.owner)
 ctx.set_option(pem.OPT_STEP1_PATH, a.step1)
 ctx.set_option(pem.OPT_STEP2_KERNEL, a.step2)
 ctx.set_option(pem.OPT_SIZE_PLANS, a.plans)
+ctx.set_option(pem.OPT_GRAPHS, a.graphs)
 for k in a.configs:
     t0 = time.time()
     name, tb, (rows, cols, I, J, V) = synth.config(k, small=a.small)
@@ -74,7 +76,7 @@ for k in a.configs:
     print(f"{name}: gen {tg:.1f}s nnzA {A.info.nnz} tilesA {A.info.tiles} flop {flop} | convert {tc.convert_total_ms:.2f} ms "
           f"(tile kernel {tc.convert_kernel_ms:.3f}) | C tiles {info.tiles} pairs {info.pairs} nnz {info.nnz} tile_products {info.tile_products} | "
           f"step1 {best.step1_ms:.3f} step2 {best.step2_ms:.3f} step3 {best.step3_ms:.3f} total {best.total_ms:.3f} ms "
-          f"=> {2*flop/best.total_ms/1e6:.1f} GFLOP/s | pool {ctx.pool_bytes/2**30:.2f} GiB", flush=True)
+          f"=> {2*flop/best.total_ms/1e6:.1f} GFLOP/s | pool {ctx.pool_bytes/2**30:.2f} GiB | graph launches {ctx.graph_replays}", flush=True)
     if a.check:
         from oracle import host
         oA, oB, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)

@@ -275,7 +275,7 @@ k_col_views(int cnt, const uint32_t* __restrict__ tile_nnz_ptr, const uint16_t* 
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
         const unsigned m = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-        rec[c] = m | (run << 16);
+        rec[c] = m | (run << 24);       // offset in the top byte: disjoint from the row records' byte (bits 16-23), see step3.cu
         run += __popc(m);
     }
     uint4* out = reinterpret_cast<uint4*>(col_rec + (size_t)t * 16);
@@ -289,7 +289,7 @@ k_col_views(int cnt, const uint32_t* __restrict__ tile_nnz_ptr, const uint16_t* 
         const unsigned rc = rc_idx[x];
         const unsigned r = rc >> 4, c = rc & 15u;
         const unsigned cr = my[c];
-        vals_t[s + (cr >> 16) + __popc(cr & ((1u << r) - 1u))] = vals[x];
+        vals_t[s + (cr >> 24) + __popc(cr & ((1u << r) - 1u))] = vals[x];
     }
 }
 

@@ -198,7 +198,7 @@ struct pem_tiled {
     // step-3 views, built on first use (pem_tiled_build_views): one 32-bit record per tile row /
     // tile column = mask | first-value offset << 16, and the values in column-major order inside a tile
     uint32_t* row_rec = nullptr;      // [tiles*16]  masks[i]   | row_ptr[i] << 16          (operand A)
-    uint32_t* col_rec = nullptr;      // [tiles*16]  masks_t[i] | first value of column << 16 (operand B)
+    uint32_t* col_rec = nullptr;      // [tiles*16]  masks_t[i] | first value of column << 24 (operand B)
     double* vals_t = nullptr;         // [nnz] tile-major, column-major inside a tile        (operand B)
 };
 

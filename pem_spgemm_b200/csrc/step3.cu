@@ -28,16 +28,19 @@
 
 namespace {
 
-// all products of one (A tile row record, B tile column record) combination, ascending k
-// (ao, bo = index of the tiles' first values; value indices stay 32-bit: one IMAD.WIDE per load)
+// all products of one (A tile row record, B tile column record) combination, ascending k.
+// Records (pem_tiled_build_views): A row record = row mask | first-value offset << 16 (offset < 256: bits 16-23),
+// B column record = column mask | first-value offset << 24.  The two offsets sit in different bytes, so the AND of
+// two records IS the intersection of the masks: one LOP3 yields the common k's and the "any?" predicate.
+// (ao, bo = index of the tiles' first values)
 template <class T>
 __device__ __forceinline__ T pair_products(unsigned ar, unsigned bc, unsigned ao, unsigned bo,
                                            const T* __restrict__ A_vals, const T* __restrict__ B_vals_t, T acc)
 {
-    unsigned m = ar & bc & 0xFFFFu;
+    unsigned m = ar & bc;
     if (m) {
         const unsigned ia = ao + (ar >> 16);             // row r of the A tile
-        const unsigned ib = bo + (bc >> 16);             // column c of the B tile (values column-major)
+        const unsigned ib = bo + (bc >> 24);             // column c of the B tile (values column-major)
         do {
             const unsigned low = m & (0u - m);
             m ^= low;
@@ -46,6 +49,42 @@ __device__ __forceinline__ T pair_products(unsigned ar, unsigned bc, unsigned ao
         } while (m);
     }
     return acc;
+}
+
+// the same for the window kernel's product loop, with the two row / column base ADDRESSES pinned in 64-bit
+// registers (the empty asm keeps ptxas from re-deriving them from 32-bit indices every trip): per value one
+// LOP3, one POPC, one IMAD.WIDE (rank * sizeof(T) + base) and the load
+// (vsz = sizeof(T) as a KERNEL ARGUMENT: with an immediate ptxas turns the multiply-add into a two-instruction shift-add)
+template <class T>
+__device__ __forceinline__ T pair_products_based(unsigned m, unsigned ar, unsigned bc, unsigned ao, unsigned bo,
+                                                 const T* __restrict__ A_vals, const T* __restrict__ B_vals_t, unsigned vsz, T acc)
+{
+    unsigned long long pa = reinterpret_cast<unsigned long long>(A_vals + (ao + (ar >> 16)));
+    unsigned long long pb = reinterpret_cast<unsigned long long>(B_vals_t + (bo + (bc >> 24)));
+    asm volatile("" : "+l"(pa), "+l"(pb));
+    do {
+        const unsigned low = m & (0u - m);
+        m ^= low;
+        const unsigned lt = low - 1u;
+        unsigned long long xa, xb;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(xa) : "r"(__popc(ar & lt)), "r"(vsz), "l"(pa));
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(xb) : "r"(__popc(bc & lt)), "r"(vsz), "l"(pb));
+        acc = fma(__ldg(reinterpret_cast<const T*>(xa)), __ldg(reinterpret_cast<const T*>(xb)), acc);
+    } while (m);
+    return acc;
+}
+
+__device__ __forceinline__ unsigned lds_u32(uint32_t addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
 }
 
 // one C nonzero (r, c) of a tile with pairs [ps, pe): the candidate pairs come from the hit blocks
@@ -169,10 +208,10 @@ k_step3_classes(int64_t n_tiles, int small_e, int small_np,
                 double acc = 0.0;
                 for (int j = 0; j < npi; ++j, sa += 32, sb += 32, ++so) {
                     const unsigned ar = *sa, bc = *sb;
-                    unsigned m = active ? (ar & bc & 0xFFFFu) : 0u;
+                    unsigned m = active ? (ar & bc) : 0u;
                     if (m) {
                         const uint2 o = *so;
-                        const unsigned ia = o.x + (ar >> 16), ib = o.y + (bc >> 16);     // 32-bit value indices
+                        const unsigned ia = o.x + (ar >> 16), ib = o.y + (bc >> 24);     // 32-bit value indices
                         do {
                             const unsigned low = m & (0u - m);
                             m ^= low;
@@ -361,11 +400,12 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
                 const int2* __restrict__ pairs, const uint32_t* __restrict__ hit_t,
                 const uint32_t* __restrict__ A_off, const T* __restrict__ A_vals, const uint4* __restrict__ A_row_rec4,
                 const uint32_t* __restrict__ B_off, const T* __restrict__ B_vals_t, const uint4* __restrict__ B_col_rec4,
-                T* __restrict__ C_vals)
+                T* __restrict__ C_vals, unsigned vsz)
 {
     static_assert(SCAP % 16 == 0 && SCAP >= NP && (SCAP + 31) / 32 <= S3W_THREADS / 32 && NP <= 128, "window shape");
     using L = S3WLayout<NP, SCAP, ECAP>;
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    static_assert(L::REC == 0, "the pair loop derives the staged pair index from the record's byte offset");
+    extern __shared__ __align__(128) unsigned char s_raw[];
     uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_raw + L::REC);     // pair j: A row records [32j .. 32j+15], B column records [32j+16 .. 32j+31]
     uint2* s_voff = reinterpret_cast<uint2*>(s_raw + L::VOFF);         // pair j: first value of the A tile, of the B tile
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_raw + L::MASK);
@@ -374,6 +414,7 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
     uint16_t* s_code = reinterpret_cast<uint16_t*>(s_raw + L::CODE);
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = smem_addr(s_raw);                            // 128-byte aligned
     const int64_t ta = win_tile[blockIdx.x], tb = win_tile[blockIdx.x + 1];
     const int nt = (int)(tb - ta);
     if (nt <= 0) return;                                        // a hub tile spans this whole window
@@ -418,12 +459,21 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
             if (word) {
                 int rank = s_nz[it >> 3] + (incl - pc) - e0;
                 const unsigned base = (unsigned)(it >> 3) << 8 | (unsigned)(it & 7) << 5;
-                do {
-                    const unsigned b = __ffs(word) - 1;
-                    word &= word - 1;
-                    if ((unsigned)rank < (unsigned)ECAP) s_code[rank] = (uint16_t)(base + b);
-                    ++rank;
-                } while (word);
+                if (ne <= ECAP) {                       // one pass (the usual case): every rank is in range
+                    uint16_t* dst = s_code + rank;
+                    do {
+                        const unsigned b = __ffs(word) - 1;
+                        word &= word - 1;
+                        *dst++ = (uint16_t)(base + b);
+                    } while (word);
+                } else {
+                    do {
+                        const unsigned b = __ffs(word) - 1;
+                        word &= word - 1;
+                        if ((unsigned)rank < (unsigned)ECAP) s_code[rank] = (uint16_t)(base + b);
+                        ++rank;
+                    } while (word);
+                }
             }
         }
         if (e0 == 0) asm volatile("cp.async.wait_all;" ::: "memory");
@@ -432,22 +482,28 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
         const int e1 = min(ne, e0 + ECAP);
         for (int i = e0 + tid; i < e1; i += S3W_THREADS) {
             const unsigned code = s_code[i - e0];
-            const unsigned tl = code >> 8, r = (code >> 4) & 15u, c = code & 15u;
+            const unsigned tl = code >> 8;
             const int js = s_pp[tl], je = s_pp[tl + 1];
             T acc = 0;
             if (je <= ns) {
-                const uint32_t* ra = s_rec + js * 32 + r;
-                const uint32_t* rb = s_rec + js * 32 + 16 + c;
-                const uint2* vo = s_voff + js;
-                for (int j = js; j < je; ++j, ra += 32, rb += 32, ++vo) {
-                    const unsigned ar = *ra, bc = *rb;
-                    if (ar & bc & 0xFFFFu) {
-                        const uint2 o = *vo;
+                // the pair loop runs on three shared-memory ADDRESSES (A row record, B column record, value offsets of the
+                // current pair) and one compare; a hit is one LOP3 (the records' offsets sit in disjoint bytes)
+                uint32_t ra = sbase + (unsigned)js * 128u + ((code >> 2) & 0x3Cu);
+                uint32_t rb = sbase + (unsigned)js * 128u + 64u + ((code & 15u) << 2);
+                uint32_t va = sbase + L::VOFF + (unsigned)js * 8u;
+                const uint32_t ra_end = ra + (unsigned)(je - js) * 128u;
+                while (ra != ra_end) {
+                    const unsigned ar = lds_u32(ra), bc = lds_u32(rb);
+                    if (ar & bc) {
+                        const uint2 o = lds_v2(va);
                         acc = pair_products<T>(ar, bc, o.x, o.y, A_vals, B_vals_t, acc);
                     }
+                    ra += 128u;
+                    rb += 128u;
+                    va += 8u;
                 }
             } else {
-                acc = entry_by_hits<T>(r, c, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
+                acc = entry_by_hits<T>((code >> 4) & 15u, code & 15u, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
                                        A_off, A_vals, reinterpret_cast<const uint32_t*>(A_row_rec4),
                                        B_off, B_vals_t, reinterpret_cast<const uint32_t*>(B_col_rec4));
             }
@@ -479,7 +535,7 @@ static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, 
         win_tile, C->tile_nnz_ptr, reinterpret_cast<const uint4*>(C->masks), C->pair_ptr, C->pair_list, C->pair_hit,
         A->tile_nnz_ptr, reinterpret_cast<const T*>(A->vals), reinterpret_cast<const uint4*>(A->row_rec),
         B->tile_nnz_ptr, reinterpret_cast<const T*>(B->vals_t), reinterpret_cast<const uint4*>(B->col_rec),
-        reinterpret_cast<T*>(C->vals));
+        reinterpret_cast<T*>(C->vals), (unsigned)sizeof(T));
     KT_END(KT_NUMERIC);
     PEM_LAUNCHED();
     pem_free(ctx, win_tile);

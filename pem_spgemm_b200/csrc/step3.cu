@@ -42,9 +42,9 @@ __device__ __forceinline__ T pair_products(unsigned ar, unsigned bc, unsigned ao
         const unsigned ia = ao + (ar >> 16);             // row r of the A tile
         const unsigned ib = bo + (bc >> 24);             // column c of the B tile (values column-major)
         do {
-            const unsigned low = m & (0u - m);
-            m ^= low;
-            const unsigned lt = low - 1u;                // lt < 2^16: the offset bits drop out of the ranks
+            const unsigned t = m - 1u;
+            const unsigned lt = ~m & t;                  // the bits below the lowest common k (lt < 2^16: the offset bits drop out of the ranks)
+            m &= t;
             acc = fma(A_vals[ia + __popc(ar & lt)], B_vals_t[ib + __popc(bc & lt)], acc);
         } while (m);
     }

@@ -213,6 +213,7 @@ struct pem_result {
     int64_t tiles = 0, pairs = 0, nnz = 0, tile_products = 0;
     int stage = 0;                    // 1, 2, 3 = last completed step
     bool s3_entries = false;          // step 3 runs the entry-owner kernel (PEM_OPT_OWNER = 2)
+    bool s2_pairs = false;            // step 2 ran the pair kernel (pair_hit may still be null: dense-tile mode, see pem_step2_symbolic)
     int64_t* row_ptr = nullptr;       // [re-rb+1]
     int32_t* tile_row = nullptr;      // [tiles]
     int32_t* tile_col = nullptr;      // [tiles]

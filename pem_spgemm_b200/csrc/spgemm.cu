@@ -141,7 +141,9 @@ k_pairblock_tiles(int64_t n_tiles, const int64_t* __restrict__ pair_ptr, int32_t
 // B's rows in its own shared-memory column (conflict-free, read back only by the lane that wrote them) and
 // forms prod[rows 2w, 2w+1] in a REGISTER per A mask word: one shared-memory load per A nonzero, nothing else
 // touches the load/store unit (the list form was bound by it: 91 % of the L1 throughput on config 4).
-template <bool ROWS>
+// HITS = false (dense-tile mode: row form and step 3 is going to be the window kernel, which finds its pairs in shared
+// memory): no hit words, no transposes, nothing stored per pair.
+template <bool ROWS, bool HITS>
 __global__ void __launch_bounds__(S2P_THREADS, 2048 / S2P_THREADS)
 k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_tile,
               const int64_t* __restrict__ pair_ptr, const int2* __restrict__ pairs,
@@ -250,19 +252,19 @@ k_step2_pairs(int64_t n_pairs, int64_t n_tiles, const int32_t* __restrict__ blk_
 #pragma unroll
         for (int w = 0; w < 8; ++w) acc[w] = s_acc[w * S2P_THREADS + tid];
     }
-    unsigned hit = 0;
-    {
-        unsigned c = 0, rows_hit = 0;
+    if (HITS) {
+        unsigned hit = 0;
+        {
+            unsigned c = 0, rows_hit = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            c |= acc[w];
-            rows_hit |= ((acc[w] & 0xFFFFu) ? 1u : 0u) << (2 * w);
-            rows_hit |= ((acc[w] >> 16) ? 1u : 0u) << (2 * w + 1);
+            for (int w = 0; w < 8; ++w) {
+                c |= acc[w];
+                rows_hit |= ((acc[w] & 0xFFFFu) ? 1u : 0u) << (2 * w);
+                rows_hit |= ((acc[w] >> 16) ? 1u : 0u) << (2 * w + 1);
+            }
+            hit = (rows_hit << 16) | ((c | (c >> 16)) & 0xFFFFu);
         }
-        hit = (rows_hit << 16) | ((c | (c >> 16)) & 0xFFFFu);
-    }
-    // 32x32 bit transpose across the warp: afterwards lane b holds bit b of every lane's hit word
-    {
+        // 32x32 bit transpose across the warp: afterwards lane b holds bit b of every lane's hit word
         unsigned v = hit, m = 0x0000FFFFu;
 #pragma unroll
         for (int j = 16; j > 0; j >>= 1) {
@@ -420,10 +422,20 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
     } else {
         const int64_t nblk = (C->pairs + S2P_THREADS - 1) / S2P_THREADS;
         if (nblk > 0x7fffffffLL) return ctx->fail(PEM_ERR_LIMIT, "more than 2^39 tile pairs");
-        PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)nblk * S2P_THREADS));
         // one lane per pair by default; sixteen lanes per C' tile (k_step2_tiles) on request: measured on B200 it
         // loses even on the stencil product it was written for (config 4: 7.1 ms against 3.4 ms)
         const bool by_tiles = ctx->opt_step2_kernel == 2;
+        // row form for dense tiles (at least eight nonzeros per A tile on average; config 4: 17.9), list form otherwise
+        // (hypersparse tiles: one or two list steps per pair; hub tiles walk the shorter of the two lists)
+        const bool rows_form = ctx->opt_step2_kernel == 3 ||
+                               (ctx->opt_step2_kernel == 0 && A->nnz >= 8 * (int64_t)A->tiles);
+        // dense-tile mode: both operands' tiles are dense and the numeric kernel is left to the engine (or is the window
+        // kernel): step 3 will run the window kernel, whose pairs sit in shared memory, so the per-pair hit words (a
+        // ninth of this kernel's instructions and 4 bytes per pair) are not produced at all
+        const bool hits = !(ctx->opt_step2_kernel == 0 && rows_form && !by_tiles && (ctx->opt_owner == 0 || ctx->opt_owner == 4) &&
+                            B->nnz >= 8 * (int64_t)B->tiles);
+        C->s2_pairs = true;
+        if (hits) PEM_TRY(pem_alloc(ctx, &C->pair_hit, (size_t)nblk * S2P_THREADS));
         if (by_tiles && C->pairs > 0) {
             pem_free(ctx, C->pair_blk);
             KT_BEGIN(KT_PAIRS);
@@ -442,15 +454,12 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
                 k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
                 PEM_LAUNCHED();
             }
-            // row form for dense tiles (at least eight nonzeros per A tile on average; config 4: 17.9), list form otherwise
-            // (hypersparse tiles: one or two list steps per pair; hub tiles walk the shorter of the two lists)
-            const bool rows_form = ctx->opt_step2_kernel == 3 ||
-                                   (ctx->opt_step2_kernel == 0 && A->nnz >= 8 * (int64_t)A->tiles);
             KT_BEGIN(KT_PAIRS);
 #define S2P_ARGS C->pairs, C->tiles, blk, C->pair_ptr, C->pair_list, A->tile_nnz_ptr, A->rc_idx, A->masks_t, A->masks, \
                 B->tile_nnz_ptr, B->rc_idx, B->masks, reinterpret_cast<uint32_t*>(C->masks), C->pair_hit
-            if (rows_form) k_step2_pairs<true><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
-            else k_step2_pairs<false><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
+            if (rows_form && !hits) k_step2_pairs<true, false><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
+            else if (rows_form) k_step2_pairs<true, true><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
+            else k_step2_pairs<false, true><<<(unsigned)nblk, S2P_THREADS, 0, ctx->stream>>>(S2P_ARGS);
 #undef S2P_ARGS
             KT_END(KT_PAIRS);
             PEM_LAUNCHED();

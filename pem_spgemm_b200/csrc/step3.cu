@@ -89,7 +89,7 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t addr)
 
 // one C nonzero (r, c) of a tile with pairs [ps, pe): the candidate pairs come from the hit blocks
 // (word 16+r of 32-pair block b has bit i set iff pair 32b+i touches C row r; word c likewise for columns)
-template <class T>
+template <class T, bool HITS = true>
 __device__ __forceinline__ T entry_by_hits(unsigned r, unsigned c, int64_t ps, int64_t pe,
                                            const int2* __restrict__ pairs, const uint32_t* __restrict__ hit_t,
                                            const uint32_t* __restrict__ A_off, const T* __restrict__ A_vals,
@@ -99,7 +99,7 @@ __device__ __forceinline__ T entry_by_hits(unsigned r, unsigned c, int64_t ps, i
 {
     T acc = 0;
     for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
-        unsigned w = hit_t[base + 16 + r] & hit_t[base + c];
+        unsigned w = HITS ? hit_t[base + 16 + r] & hit_t[base + c] : 0xFFFFFFFFu;    // no hit blocks (dense-tile mode of step 2): every pair is a candidate
         if (base < ps) w &= 0xFFFFFFFFu << (unsigned)(ps - base);
         if (base + 32 > pe) w &= 0xFFFFFFFFu >> (unsigned)(base + 32 - pe);
         while (w) {
@@ -393,7 +393,7 @@ struct S3WLayout {
     static constexpr int BYTES = CODE + ECAP * 2;
 };
 
-template <class T, int NP, int SCAP, int ECAP, int MINB>   // window pairs, staged pairs (multiple of 16), nonzeros decoded per pass
+template <class T, int NP, int SCAP, int ECAP, int MINB, bool HITS>   // window pairs, staged pairs (multiple of 16), nonzeros decoded per pass, hit blocks present
 __global__ void __launch_bounds__(S3W_THREADS, MINB)
 k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict__ c_tile_nnz_ptr,
                 const uint4* __restrict__ Cmasks128, const int64_t* __restrict__ pair_ptr,
@@ -503,9 +503,11 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
                     va += 8u;
                 }
             } else {
-                acc = entry_by_hits<T>((code >> 4) & 15u, code & 15u, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
-                                       A_off, A_vals, reinterpret_cast<const uint32_t*>(A_row_rec4),
-                                       B_off, B_vals_t, reinterpret_cast<const uint32_t*>(B_col_rec4));
+                // the window's last tile owns more pairs than are staged (hub tiles of power-law inputs, wide dense bands): through
+                // the hit blocks like the entry-owner kernel, or over every pair of the tile when step 2 produced no hit blocks
+                acc = entry_by_hits<T, HITS>((code >> 4) & 15u, code & 15u, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
+                                             A_off, A_vals, reinterpret_cast<const uint32_t*>(A_row_rec4),
+                                             B_off, B_vals_t, reinterpret_cast<const uint32_t*>(B_col_rec4));
             }
             C_vals[N0 + i] = acc;
         }
@@ -514,7 +516,7 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
 }
 
 // one window-kernel configuration: table kernel + numeric kernel
-template <class T, int NP, int SCAP, int ECAP, int MINB>
+template <class T, int NP, int SCAP, int ECAP, int MINB, bool HITS>
 static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem_result* C)
 {
     const int64_t n_windows = (C->pairs + NP - 1) / NP;
@@ -523,7 +525,7 @@ static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, 
     PEM_TRY(pem_alloc(ctx, &win_tile, (size_t)n_windows + 1));
     k_window_tiles<<<pem_div_up(C->tiles + 1, 256), 256, 0, ctx->stream>>>(C->tiles, n_windows, NP, C->pair_ptr, win_tile);
     PEM_LAUNCHED();
-    auto kern = k_step3_windows<T, NP, SCAP, ECAP, MINB>;
+    auto kern = k_step3_windows<T, NP, SCAP, ECAP, MINB, HITS>;
     constexpr int smem = S3WLayout<NP, SCAP, ECAP>::BYTES;
     static bool attr_set = false;                               // opt in to > 48 KB of dynamic shared memory (once per process)
     if (!attr_set && smem > 48 * 1024) {
@@ -646,17 +648,20 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
     PEM_CK(cudaSetDevice(ctx->device));
     PEM_TRY(pem_tiled_wait_vals(ctx, A));        // freshly converted operands: the values may still be on their way
     PEM_TRY(pem_tiled_wait_vals(ctx, B));
-    if (C->dtype == PEM_F32 && (!C->pair_hit || !C->s3_entries))
+    if (C->dtype == PEM_F32 && (!C->s2_pairs || !C->s3_entries))
         return ctx->fail(PEM_ERR_ARG, "fp32 products run the default kernels only (PEM_OPT_OWNER 0 / 2 / 4)");
     PEM_TRY(pem_alloc_bytes(ctx, (void**)&C->vals, std::max<size_t>(1, (size_t)C->nnz * pem_vsize(C->dtype))));
-    const bool by_records = C->pair_hit != nullptr;         // step 2 ran the pair kernel
+    const bool by_records = C->s2_pairs;                    // step 2 ran the pair kernel
+    // dense-tile mode of step 2 (no hit words): only the window kernel can run
+    if (by_records && !C->pair_hit && !(C->s3_entries && (ctx->opt_owner == 0 || ctx->opt_owner == 4)))
+        return ctx->fail(PEM_ERR_ARG, "step 2 ran in dense-tile mode (no hit words): set PEM_OPT_OWNER before step 2, not between steps 2 and 3");
     // the class kernel reads every nonzero's (r, c) from Ctiles_rowColIdx; the entry-owner kernel derives it
     // from the tile mask (measured on config 4: 11.6 ms against 12.7 ms with the bytes, but producing them costs 1.0 ms)
     const bool use_rc = !C->s3_entries;
     // default: the window kernel when C's tiles are dense enough that staging a pair's 128 bytes of records pays
     // (at least four nonzeros per pair: stencil / FEM products), else the entry-owner kernel
     const bool windows = by_records && C->s3_entries &&
-                         (ctx->opt_owner == 4 || (ctx->opt_owner == 0 && C->nnz >= 4 * C->pairs));
+                         (ctx->opt_owner == 4 || !C->pair_hit || (ctx->opt_owner == 0 && C->nnz >= 4 * C->pairs));
     if (C->nnz > 0 && by_records) {                          // views are cached on the handles after the first product
         PEM_TRY(pem_tiled_build_views(ctx, A, true, false));
         PEM_TRY(pem_tiled_build_views(ctx, B, false, true));
@@ -674,8 +679,12 @@ extern "C" int pem_step3_numeric(pem_ctx* ctx, const pem_tiled* A, const pem_til
         // 128-pair windows, 144 staged pairs, 1024 nonzeros per decode pass: 26 KB of shared memory and 32 registers, so
         // that eight blocks (64 warps) stay resident per SM: the kernel is bound by the latency of its value gathers, and
         // 8 blocks measured 8.9 ms on config 4 against 10.3 ms with 6 (160 staged pairs, 2048 nonzeros per pass)
-        PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 144, 1024, 8>(ctx, A, B, C))
-                                    : (launch_windows<double, 128, 144, 1024, 8>(ctx, A, B, C)));
+        if (C->pair_hit)
+            PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 144, 1024, 8, true>(ctx, A, B, C))
+                                        : (launch_windows<double, 128, 144, 1024, 8, true>(ctx, A, B, C)));
+        else
+            PEM_TRY(C->dtype == PEM_F32 ? (launch_windows<float, 128, 144, 1024, 8, false>(ctx, A, B, C))
+                                        : (launch_windows<double, 128, 144, 1024, 8, false>(ctx, A, B, C)));
         C->stage = 3;
         return PEM_OK;
     }

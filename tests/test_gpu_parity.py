@@ -72,6 +72,31 @@ def test_dense_blocks_all_step3_variants(engine):
         A.free()
 
 
+@pytest.mark.parametrize("owner,step2", [(0, 0), (4, 0), (4, 3), (2, 0), (0, 1)])
+def test_dense_tiles_with_long_pair_lists(engine, owner, step2):
+    """A wide matrix with dense tiles times its transpose: every C' tile owns 375 pairs, more than the window kernel
+    stages (144), so its nonzeros take the kernel's unstaged path: a walk over all pairs in dense-tile mode (step 2
+    automatic: no hit words are produced), the hit blocks when the row-mask form is forced or the entry-owner kernel asked for."""
+    rows, cols, I, J, V = synth.random_sparse(48, 6000, 40000, seed=21)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.transpose(A)
+    assert A.info.nnz >= 8 * A.info.tiles
+    engine.set_option(pem.OPT_OWNER, owner)
+    engine.set_option(pem.OPT_STEP2_KERNEL, step2)
+    try:
+        for _ in range(3):                            # ordinary, captured, graph launch
+            C = engine.spgemm(A, B)
+            assert C.info.pairs == 9 * 375
+            assert engine.last_step3_kernel == (2 if owner == 2 or (owner == 0 and step2 == 1 and C.info.nnz < 4 * C.info.pairs) else 4)
+            _assert_same_C(C, oC)
+            C.free()
+    finally:
+        engine.set_option(pem.OPT_OWNER, 0)
+        engine.set_option(pem.OPT_STEP2_KERNEL, 0)
+    B.free(); A.free()
+
+
 @pytest.mark.parametrize("shape,nnz,seed", SHAPES + [((16, 16), 0, 9)])
 def test_device_transpose_equals_transposed_conversion(engine, shape, nnz, seed):
     """pem_tiled_transpose (A^T from A's tiles) must reproduce pem_convert_coo(transpose=1) array by array."""

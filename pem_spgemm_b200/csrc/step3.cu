@@ -74,6 +74,19 @@ __device__ __forceinline__ T pair_products_based(unsigned m, unsigned ar, unsign
     return acc;
 }
 
+__device__ __forceinline__ unsigned lds_u32(uint32_t addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
 // Window kernel: the same products with the fma DEFERRED by one product.  A warp issues in order, so an fma placed
 // right behind its two value gathers parks the warp for a full memory latency per product (46 % of the kernel's
 // stall samples sat there).  Here the gathers of product n are issued, and consumed only when product n + 1 has
@@ -97,22 +110,9 @@ __device__ __forceinline__ void pair_products_deferred(unsigned m, unsigned ar, 
     } while (m);
 }
 
-__device__ __forceinline__ unsigned lds_u32(uint32_t addr)
-{
-    unsigned v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 lds_v2(uint32_t addr)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-
 // one C nonzero (r, c) of a tile with pairs [ps, pe): the candidate pairs come from the hit blocks
 // (word 16+r of 32-pair block b has bit i set iff pair 32b+i touches C row r; word c likewise for columns)
-template <class T, bool HITS = true>
+template <class T, bool HITS = true, bool DEFER = true>     // DEFER: fma one product behind its gathers (off in the window kernel's rare path: registers)
 __device__ __forceinline__ T entry_by_hits(unsigned r, unsigned c, int64_t ps, int64_t pe,
                                            const int2* __restrict__ pairs, const uint32_t* __restrict__ hit_t,
                                            const uint32_t* __restrict__ A_off, const T* __restrict__ A_vals,
@@ -120,7 +120,7 @@ __device__ __forceinline__ T entry_by_hits(unsigned r, unsigned c, int64_t ps, i
                                            const uint32_t* __restrict__ B_off, const T* __restrict__ B_vals_t,
                                            const uint32_t* __restrict__ B_col_rec)
 {
-    T acc = 0;
+    T acc = 0, pa = 0, pb = 0;                      // (pa, pb): operands of the product whose gathers are in flight
     for (int64_t base = ps & ~(int64_t)31; base < pe; base += 32) {
         unsigned w = HITS ? hit_t[base + 16 + r] & hit_t[base + c] : 0xFFFFFFFFu;    // no hit blocks (dense-tile mode of step 2): every pair is a candidate
         if (base < ps) w &= 0xFFFFFFFFu << (unsigned)(ps - base);
@@ -132,10 +132,15 @@ __device__ __forceinline__ T entry_by_hits(unsigned r, unsigned c, int64_t ps, i
             const unsigned ar = A_row_rec[(unsigned)ab.x * 16u + r];
             const unsigned bc = B_col_rec[(unsigned)ab.y * 16u + c];
             const unsigned ao = A_off[ab.x], bo = B_off[ab.y];      // issued with the records, not after the mask test
-            acc = pair_products(ar, bc, ao, bo, A_vals, B_vals_t, acc);
+            if (DEFER) {
+                const unsigned m = ar & bc;
+                if (m) pair_products_deferred<T>(m, ar, bc, ao, bo, A_vals, B_vals_t, acc, pa, pb);
+            } else {
+                acc = pair_products(ar, bc, ao, bo, A_vals, B_vals_t, acc);
+            }
         }
     }
-    return acc;
+    return DEFER ? fma(pa, pb, acc) : acc;
 }
 
 constexpr int S3C_THREADS = 128;      // four warps, 32 tiles each
@@ -531,7 +536,7 @@ k_step3_windows(const int32_t* __restrict__ win_tile, const int64_t* __restrict_
             } else {
                 // the window's last tile owns more pairs than are staged (hub tiles of power-law inputs, wide dense bands): through
                 // the hit blocks like the entry-owner kernel, or over every pair of the tile when step 2 produced no hit blocks
-                acc = entry_by_hits<T, HITS>((code >> 4) & 15u, code & 15u, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
+                acc = entry_by_hits<T, HITS, false>((code >> 4) & 15u, code & 15u, pair_ptr[ta + tl], pair_ptr[ta + tl + 1], pairs, hit_t,
                                              A_off, A_vals, reinterpret_cast<const uint32_t*>(A_row_rec4),
                                              B_off, B_vals_t, reinterpret_cast<const uint32_t*>(B_col_rec4));
             }

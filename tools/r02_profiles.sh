@@ -13,13 +13,14 @@ full() {   # config, launch-skip, count, extra quick_bench flags
   rm -f gpurun_out/full_${tag}_c$k.ncu-rep
   tail -n 2 gpurun_out/ncufull_${tag}_c$k.log
 }
-for k in 1 2 3 4; do bash tools/launch_list.sh $tag $k; done
-QB_FLAGS="--panels 16 --reps 1" bash tools/launch_list.sh $tag 5
+# (--graphs 0: the kernels of a product are launched one by one, so that --launch-skip counts mean what they say)
+for k in 1 2 3 4; do QB_FLAGS="--graphs 0" bash tools/launch_list.sh $tag $k; done
+QB_FLAGS="--panels 16 --reps 1 --graphs 0" bash tools/launch_list.sh $tag 5
 # kernels matched per product: bitmap path 4 (count, fill, pairs, numeric); radix path 9 (tile_products, expand, 4 x onesweep,
 # ctiles, pairs, entries); row-sort path 6 (tile_products, expand, row_sort, row_tiles, pairs, windows); + k_build_tiles per conversion
-full 1 5 4 --reps 2
-full 2 10 9 --reps 2
-full 3 11 9 --reps 2
-full 4 7 6 --reps 2
-full 5 10 9 --panels 16 --reps 1     # second panel of the first product
+full 1 5 4 --reps 2 --graphs 0
+full 2 10 9 --reps 2 --graphs 0
+full 3 11 9 --reps 2 --graphs 0
+full 4 7 6 --reps 2 --graphs 0
+full 5 10 9 --panels 16 --reps 1 --graphs 0     # second panel of the first product
 du -sh gpurun_out

@@ -111,10 +111,12 @@ typedef enum pem_option {
      * per-GPU panels of a multi-GPU run.  The graph owns the device blocks its product touches, result included: a
      * result handed out from it borrows them, and the graph runs again only after that result was freed (a product
      * called while the previous result is alive takes the ordinary path).  A product with a host stall inside, or
-     * whose blocks would take the graphs' memory past PEM_OPT_GRAPH_LIMIT_MB, silently stays on the ordinary path.
+     * whose blocks do not fit the graphs' memory budget (PEM_OPT_GRAPH_LIMIT_MB), silently stays on the ordinary path.
      * Freeing an operand drops its plans and graphs.  0: no graphs. */
     PEM_OPT_GRAPHS = 12,
-    /* budget for the device memory held by product graphs, MiB (default: a quarter of the memory free at pem_ctx_create) */
+    /* budget for the device memory held by product graphs, MiB (default: a quarter of the memory free at pem_ctx_create);
+     * a single graph may hold an eighth of it: products that move gigabytes do not wait for their launches, and the
+     * sequential panels of a large product must not park their buffers in graphs */
     PEM_OPT_GRAPH_LIMIT_MB = 13
 } pem_option;
 

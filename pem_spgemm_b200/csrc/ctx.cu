@@ -61,6 +61,7 @@ static int graph_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
 int pem_alloc_bytes(pem_ctx* ctx, void** p, size_t bytes)
 {
     bytes = (bytes + 511) & ~(size_t)511;
+    ctx->prod_alloc += bytes;
     if (ctx->cap) return graph_alloc_bytes(ctx, p, bytes);
     auto it = ctx->free_blocks.lower_bound(bytes);
     if (it != ctx->free_blocks.end() && it->first - bytes <= it->first / 4) {

@@ -32,6 +32,7 @@ struct pem_plan {
     // PEM_OPT_GRAPHS: the replayed product captured as one CUDA graph over buffers the graph owns (spgemm.cu)
     std::shared_ptr<pem_graph> graph;
     bool graph_failed = false;      // the capture was tried and given up (a host stall inside, or over the memory budget)
+    size_t alloc_bytes = 0;         // bytes the recording product asked the allocator for: upper bound of a graph's arena
 };
 // pairs per block of step 2's pair kernel; step 1 (k_ctiles) emits the first tile of every such block
 constexpr int PEM_PAIR_BLOCK = 128;
@@ -71,6 +72,7 @@ struct pem_ctx {
     pem_graph* cap = nullptr;     // graph being captured: allocations come from / go back to its arena
     size_t graph_bytes = 0, graph_limit = (size_t)8 << 30;   // bytes held by graph arenas / their budget (a quarter of the memory free at creation)
     int64_t graph_replays = 0;    // products that ran as a graph launch since creation (pem_ctx_graph_replays)
+    size_t prod_alloc = 0;        // bytes requested from the allocator by the product in flight
     int64_t size_stalls = 0;      // host stalls at size read-backs since creation (pem_ctx_size_stalls)
     int64_t* d_scalars = nullptr; // device mirror the kernels reduce into
     cudaEvent_t ev[PEM_NEVENTS] = {};

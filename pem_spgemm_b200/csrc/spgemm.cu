@@ -571,8 +571,12 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
         // below replays the plan (so it never stalls), then launched; later products launch the same graph.
         int gopts[5];
         pem_graph_opts(ctx, gopts);
+        // (one graph may hold at most an eighth of the graphs' memory budget: where a product moves gigabytes, its
+        //  launches are not what it waits for, and sequential panels of a large product must not park their buffers)
         const bool graph_ok = plan && plan->valid && ctx->opt_graphs && !plan->graph_failed && !ctx->opt_trace &&
-                              !A->vals_pending && !B->vals_pending;
+                              !A->vals_pending && !B->vals_pending &&
+                              (plan->graph || plan->alloc_bytes <= ctx->graph_limit / 8);
+        ctx->prod_alloc = 0;
         std::shared_ptr<pem_graph> g;
         bool launch_only = false, capture = false;
         if (graph_ok && plan->graph) {
@@ -667,6 +671,7 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
         if (!replayed) {
             pl->n = npos;
             pl->valid = true;
+            pl->alloc_bytes = ctx->prod_alloc;
             break;
         }
         bool same = npos == pl->n;

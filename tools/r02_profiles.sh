@@ -20,7 +20,7 @@ QB_FLAGS="--panels 16 --reps 1 --graphs 0" bash tools/launch_list.sh $tag 5
 # ctiles, pairs, entries); row-sort path 6 (tile_products, expand, row_sort, row_tiles, pairs, windows); + k_build_tiles per conversion
 full 1 5 4 --reps 2 --graphs 0
 full 2 10 9 --reps 2 --graphs 0
-full 3 11 9 --reps 2 --graphs 0
+full 3 12 9 --reps 2 --graphs 0
 full 4 7 6 --reps 2 --graphs 0
 full 5 10 9 --panels 16 --reps 1 --graphs 0     # second panel of the first product
 du -sh gpurun_out

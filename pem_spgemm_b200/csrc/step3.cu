@@ -5,9 +5,11 @@
 // value bits agree; C is written exactly once (the reference read-modify-writes global C per product and
 // never zeroes it) and no floating-point atomic exists.
 //
-// Default kernel: k_step3_entries, one thread per C nonzero over the flat nonzero index space: every lane
-// of every warp owns one nonzero whatever the tile sizes are, which no tile-granular mapping matched on the
-// five BASELINE shapes (profiles/r02_summary.md).
+// Default kernels (chosen per product, pem_step3_numeric): k_step3_windows for dense-tile products (stencil / FEM:
+// a block per 128-pair window, the pairs' records staged in shared memory) and k_step3_entries for hypersparse
+// tiles (one thread per C nonzero over the flat nonzero index space: every lane of every warp owns one nonzero
+// whatever the tile sizes are).  Both defer the fma by one product, so that a warp is not parked behind every
+// pair of value gathers (profiles/r02_step3_windows.md).
 //
 // Selectable (PEM_OPT_OWNER = 3) and bit-identical: k_step3_classes.  A warp takes 32 consecutive C' tiles;
 // their offsets are read coalesced and every tile is handled by the mapping its size calls for:
@@ -48,29 +50,6 @@ __device__ __forceinline__ T pair_products(unsigned ar, unsigned bc, unsigned ao
             acc = fma(A_vals[ia + __popc(ar & lt)], B_vals_t[ib + __popc(bc & lt)], acc);
         } while (m);
     }
-    return acc;
-}
-
-// the same for the window kernel's product loop, with the two row / column base ADDRESSES pinned in 64-bit
-// registers (the empty asm keeps ptxas from re-deriving them from 32-bit indices every trip): per value one
-// LOP3, one POPC, one IMAD.WIDE (rank * sizeof(T) + base) and the load
-// (vsz = sizeof(T) as a KERNEL ARGUMENT: with an immediate ptxas turns the multiply-add into a two-instruction shift-add)
-template <class T>
-__device__ __forceinline__ T pair_products_based(unsigned m, unsigned ar, unsigned bc, unsigned ao, unsigned bo,
-                                                 const T* __restrict__ A_vals, const T* __restrict__ B_vals_t, unsigned vsz, T acc)
-{
-    unsigned long long pa = reinterpret_cast<unsigned long long>(A_vals + (ao + (ar >> 16)));
-    unsigned long long pb = reinterpret_cast<unsigned long long>(B_vals_t + (bo + (bc >> 24)));
-    asm volatile("" : "+l"(pa), "+l"(pb));
-    do {
-        const unsigned low = m & (0u - m);
-        m ^= low;
-        const unsigned lt = low - 1u;
-        unsigned long long xa, xb;
-        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(xa) : "r"(__popc(ar & lt)), "r"(vsz), "l"(pa));
-        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(xb) : "r"(__popc(bc & lt)), "r"(vsz), "l"(pb));
-        acc = fma(__ldg(reinterpret_cast<const T*>(xa)), __ldg(reinterpret_cast<const T*>(xb)), acc);
-    } while (m);
     return acc;
 }
 
@@ -382,12 +361,16 @@ k_step3_entries(int64_t nnz, int64_t n_tiles, const int32_t* __restrict__ blk_ti
 // No per-thread tile search, no rank select, no hit words; the dependent chain of the entry-owner kernel
 // (tile offset -> mask -> hit words -> pair -> records -> values, paid per nonzero with a global-memory
 // latency each) becomes window -> pairs -> records, taken once per window with all loads of a stage in
-// flight together, then values.  The window's last tile may own more pairs than are staged (hub tiles of
-// power-law inputs): it is computed through the hit blocks like the entry-owner kernel does.
+// flight together, then values.  The pair loop runs on three shared-memory addresses and tests a pair with one
+// LOP3 (record offsets in disjoint bytes); the fma runs one product behind its gathers.  The window's last tile
+// may own more pairs than are staged (hub tiles of power-law inputs, wide dense bands): it is computed through the
+// hit blocks like the entry-owner kernel does, or, when step 2 ran in dense-tile mode and left none (HITS = false),
+// by testing every pair of the tile.
 // Measured and rejected (profiles/r02_step3_windows.md): the tiles' VALUES staged in shared memory as well
 // (8-byte cp.async, packed per warp: the ~65 instructions per pair of the copy loop cost more than the
-// load stalls they remove, 19.1 ms against 11.2 ms on config 4) and 1-D bulk copies (cp.async.bulk) for the
-// per-pair payloads (a warp issues them one lane at a time, ~36 ns per copy, tools/ubench/bulk_rate.cu).
+// load stalls they remove, 19.1 ms against 11.2 ms on config 4), 1-D bulk copies (cp.async.bulk) for the
+// per-pair payloads (a warp issues them one lane at a time, ~36 ns per copy, tools/ubench/bulk_rate.cu), value base
+// addresses pinned in 64-bit registers, streaming hints, the unstaged path out of line.
 // =========================================================================================
 constexpr int S3W_THREADS = 256;
 

@@ -629,6 +629,7 @@ int pem_spgemm_panel(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B,
                 (void)cudaGetLastError();
                 graph_dissolve(ctx, g.get(), nullptr);
                 if (C) { result_forget_buffers(C); delete C; C = nullptr; }
+                ctx->launches = launches0;              // nothing of the abandoned capture ran
                 plan->graph_failed = true;
                 ctx->err.clear();
                 ctx->plan = nullptr;

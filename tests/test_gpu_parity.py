@@ -529,6 +529,39 @@ def test_product_graphs_replay_bit_identical(engine, k, step1_path):
     B.free(); A.free()
 
 
+@pytest.mark.parametrize("k", [1, 4, 2])
+def test_abandoned_graph_capture_falls_back(engine, k):
+    """A capture that cannot complete is given up and the product redone the ordinary way: here the recording product
+    ran the row-owner kernels (no step-3 views on the operands), so the capture of the next product would have to build
+    the operands' views out of a graph arena, which the engine refuses."""
+    name, tb, (rows, cols, I, J, V) = synth.config(k, small=True)
+    A = engine.convert_coo(rows, cols, I, J, V)
+    B = engine.convert_coo(rows, cols, I, J, V, transpose=tb)
+    _, _, oC = host.spgemm_from_coo(rows, cols, I, J, V, tb)
+    engine.set_option(pem.OPT_GRAPHS, 1)
+    engine.set_option(pem.OPT_OWNER, 1)
+    try:
+        C = engine.spgemm(A, B)
+        _assert_same_C(C, oC)
+        C.free()
+        engine.set_option(pem.OPT_OWNER, 0)
+        l0 = engine.launch_count
+        C = engine.spgemm(A, B)                       # ordinary path with the default kernels, after the abandoned capture
+        per_product = engine.launch_count - l0
+        for rep in range(3):
+            g1, s1, l1 = engine.graph_replays, engine.size_stalls, engine.launch_count
+            _assert_same_C(C, oC)
+            C.free()
+            C = engine.spgemm(A, B)
+            assert engine.graph_replays == g1 and engine.size_stalls == s1      # no graph for this plan, sizes still replayed
+            assert engine.launch_count - l1 <= per_product                        # (the first one also built the views)
+        _assert_same_C(C, oC)
+        C.free()
+    finally:
+        engine.set_option(pem.OPT_OWNER, 0)
+    B.free(); A.free()
+
+
 @pytest.mark.parametrize("owner", [1, 2, 3, 4])
 @pytest.mark.parametrize("k", [1, 2, 3, 4])
 def test_owner_variants_are_bit_identical(engine, k, owner):

@@ -412,6 +412,8 @@ int tile_row_flops(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, unsigne
 {
     uint32_t* b_row_nnz = nullptr;
     unsigned long long* trf = nullptr;
+    pem_guard<uint32_t> nnz_guard(ctx, b_row_nnz);
+    pem_guard<unsigned long long> trf_guard(ctx, trf);     // handed to the caller on success (nulled below)
     PEM_TRY(pem_alloc(ctx, &b_row_nnz, (size_t)B->tile_rows * 16));
     PEM_TRY(pem_alloc(ctx, &trf, (size_t)A->tile_rows));
     PEM_CK(cudaMemsetAsync(b_row_nnz, 0, (size_t)(B->tile_rows ? B->tile_rows : 1) * 16 * 4, ctx->stream));
@@ -427,6 +429,7 @@ int tile_row_flops(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, unsigne
     }
     pem_free(ctx, b_row_nnz);
     *d_out = trf;
+    trf = nullptr;
     return PEM_OK;
 }
 

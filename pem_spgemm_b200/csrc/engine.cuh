@@ -151,6 +151,18 @@ static inline void pem_free(pem_ctx* ctx, T*& p)
     p = nullptr;
 }
 
+// a local temporary that goes back to the cache on EVERY return path (the PEM_TRY / PEM_CK early returns included);
+// the success path keeps its explicit pem_free, which nulls the pointer, so nothing is freed twice or later than before
+template <class T>
+struct pem_guard {
+    pem_ctx* ctx;
+    T*& p;
+    pem_guard(pem_ctx* c, T*& q) : ctx(c), p(q) {}
+    ~pem_guard() { pem_free(ctx, p); }
+    pem_guard(const pem_guard&) = delete;
+    pem_guard& operator=(const pem_guard&) = delete;
+};
+
 static inline uint64_t pem_next_uid()
 {
     static std::atomic<uint64_t> next{1};

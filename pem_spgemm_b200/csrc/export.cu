@@ -100,8 +100,10 @@ int pem_result_to_coo_device(pem_ctx* ctx, const pem_result* C, int32_t* d_rows,
     PEM_CK(cudaSetDevice(ctx->device));
     const int ntr = C->re - C->rb;
     const size_t nrow = (size_t)ntr * 16;
-    int64_t* rp = d_row_ptr;
-    if (!rp) PEM_TRY(pem_alloc(ctx, &rp, nrow + 1));
+    int64_t* own_rp = nullptr;                 // the row pointer is a temporary unless the caller wants it
+    pem_guard<int64_t> rp_guard(ctx, own_rp);
+    if (!d_row_ptr) PEM_TRY(pem_alloc(ctx, &own_rp, nrow + 1));
+    int64_t* rp = d_row_ptr ? d_row_ptr : own_rp;
     PEM_CK(cudaMemsetAsync(rp, 0, (nrow + 1) * 8, ctx->stream));
     if (ntr > 0 && C->tiles > 0) {
         k_export_count<<<pem_div_up((int64_t)ntr * 16, 256), 256, 0, ctx->stream>>>(ntr, C->row_ptr, C->masks, rp);
@@ -118,7 +120,7 @@ int pem_result_to_coo_device(pem_ctx* ctx, const pem_result* C, int32_t* d_rows,
                 ntr, C->rb, C->row_ptr, C->tile_col, C->masks, C->tile_nnz_ptr, C->vals, rp, d_rows, d_cols, d_vals);
         PEM_LAUNCHED();
     }
-    if (!d_row_ptr) pem_free(ctx, rp);
+    pem_free(ctx, own_rp);
     return PEM_OK;
 }
 
@@ -195,6 +197,7 @@ int pem_result_checksum(pem_ctx* ctx, const pem_result* C, double* sum, double* 
     PEM_CK(cudaSetDevice(ctx->device));
     const int nb = 1024;
     double* part = nullptr;
+    pem_guard<double> part_guard(ctx, part);
     PEM_TRY(pem_alloc(ctx, &part, (size_t)2 * nb));
     if (C->dtype == PEM_F32) k_checksum_partial<float><<<nb, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(C->vals), C->nnz, part);
     else k_checksum_partial<double><<<nb, 256, 0, ctx->stream>>>(C->vals, C->nnz, part);

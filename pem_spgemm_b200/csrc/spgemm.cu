@@ -449,6 +449,7 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
             PEM_CK(cudaMemsetAsync(C->masks, 0, (size_t)C->tiles * 32, ctx->stream));
             int32_t* blk = C->pair_blk;            // expand-sort-compress leaves it behind (k_ctiles)
             C->pair_blk = nullptr;
+            pem_guard<int32_t> blk_guard(ctx, blk);
             if (!blk) {
                 PEM_TRY(pem_alloc(ctx, &blk, (size_t)nblk + 1));
                 k_pairblock_tiles<<<pem_div_up(C->tiles, 256), 256, 0, ctx->stream>>>(C->tiles, C->pair_ptr, blk);
@@ -473,6 +474,7 @@ int pem_step2_symbolic(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, pem
         size_t tb = 0;
         PEM_CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nnz_it, C->tile_nnz_ptr, C->tiles + 1, ctx->stream));
         char* tmp = nullptr;
+        pem_guard<char> tmp_guard(ctx, tmp);
         PEM_TRY(pem_alloc(ctx, &tmp, tb));
         PEM_CK(cub::DeviceScan::ExclusiveSum(tmp, tb, nnz_it, C->tile_nnz_ptr, C->tiles + 1, ctx->stream));
         ctx->launches += 2;

@@ -304,6 +304,12 @@ int pem_mtx_read(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz,
 int pem_mtx_write(const char* path, int32_t rows, int32_t cols, int64_t nnz,
                   const int32_t* I, const int32_t* J, const double* V);
 void pem_free_host(void* p);
+/* One number per line, formatted on all host threads: the ROWS / COLS / VALS files of the reference's COO dump
+ * (spgemm.cu:1545-1560, one `<<` per line there).  Doubles in fixed notation with 17 decimals, the digits
+ * `std::fixed << std::setprecision(max_digits10)` prints (:1529).  append != 0 continues an existing file
+ * (a result dumped panel by panel); otherwise the file is created or truncated. */
+int pem_write_lines_i32(const char* path, const int32_t* x, int64_t n, int append);
+int pem_write_lines_f64(const char* path, const double* x, int64_t n, int append);
 
 #ifdef __cplusplus
 }

@@ -85,7 +85,7 @@ EXPORTS = [
     "pem_spgemm", "pem_spgemm_panel", "pem_step1_symbolic", "pem_step2_symbolic", "pem_step3_numeric",
     "pem_result_info_get", "pem_result_free", "pem_result_get", "pem_result_device_ptr",
     "pem_result_to_coo", "pem_result_to_coo_f32", "pem_result_to_csr", "pem_result_to_coo_device", "pem_result_checksum", "pem_mtx_read", "pem_mtx_write",
-    "pem_free_host",
+    "pem_free_host", "pem_write_lines_i32", "pem_write_lines_f64",
 ]
 
 _lib = None
@@ -153,6 +153,8 @@ def load():
         "pem_mtx_read": (C.c_int, [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(vp),
                                    C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
         "pem_mtx_write": (C.c_int, [C.c_char_p, i32, i32, i64, vp, vp, vp]),
+        "pem_write_lines_i32": (C.c_int, [C.c_char_p, vp, i64, C.c_int]),
+        "pem_write_lines_f64": (C.c_int, [C.c_char_p, vp, i64, C.c_int]),
         "pem_free_host": (None, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -420,6 +422,18 @@ def mtx_write(path: str, rows: int, cols: int, I, J, V) -> None:
     I = np.ascontiguousarray(I, np.int32); J = np.ascontiguousarray(J, np.int32)
     V = np.ascontiguousarray(V, np.float64)
     rc = load().pem_mtx_write(path.encode(), rows, cols, I.size, _ptr(I), _ptr(J), _ptr(V))
+    if rc != PEM_OK:
+        raise PemError(rc, f"cannot write {path}")
+
+
+def write_lines(path: str, x, append: bool = False) -> None:
+    """One number per line, the format of the reference's COO dump files (int32 as is, float64 fixed with 17 decimals)."""
+    x = np.ascontiguousarray(x)
+    if x.dtype == np.float64:
+        rc = load().pem_write_lines_f64(path.encode(), _ptr(x), x.size, int(append))
+    else:
+        x = np.ascontiguousarray(x, np.int32)
+        rc = load().pem_write_lines_i32(path.encode(), _ptr(x), x.size, int(append))
     if rc != PEM_OK:
         raise PemError(rc, f"cannot write {path}")
 

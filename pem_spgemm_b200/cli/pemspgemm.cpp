@@ -35,30 +35,6 @@ static int env_int(const char* name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
-// One value per line, formatted with to_chars into a large buffer and written in a few fwrite calls (the
-// reference streams one `<<` per line, spgemm.cu:1549-1558, which is slower than the SpGEMM by orders of
-// magnitude).  Doubles: fixed notation, max_digits10 = 17 decimals, the digits `std::fixed <<
-// setprecision(17)` prints.
-struct LineWriter {
-    FILE* f;
-    std::vector<char> buf;
-    size_t n = 0;
-    bool ok;
-    explicit LineWriter(const std::string& path) : f(fopen(path.c_str(), "wb")), buf((size_t)1 << 22), ok(f != nullptr) {}
-    ~LineWriter() { close(); }
-    void flush() { if (f && n) { ok = ok && fwrite(buf.data(), 1, n, f) == n; n = 0; } }
-    char* room(size_t need) { if (n + need > buf.size()) flush(); return buf.data() + n; }
-    void put(int32_t x) { char* p = room(16); auto r = std::to_chars(p, p + 15, x); *r.ptr++ = '\n'; n += (size_t)(r.ptr - p); }
-    void put(double x)
-    {
-        char* p = room(400);
-        auto r = std::to_chars(p, p + 399, x, std::chars_format::fixed, std::numeric_limits<double>::max_digits10);
-        *r.ptr++ = '\n';
-        n += (size_t)(r.ptr - p);
-    }
-    bool close() { flush(); if (f) { ok = ok && fclose(f) == 0; f = nullptr; } return ok; }
-};
-
 #define DIE_IF(rc, ctx, what)                                                              \
     do {                                                                                   \
         if ((rc) != PEM_OK) {                                                              \
@@ -222,7 +198,10 @@ int main(int argc, char* argv[])
         out.open(dir + "/SPGEMM_RESULT_NNZ.txt");
         out << ic.nnz;                                   // no trailing newline (spgemm.cu:1546)
         out.close();
-        LineWriter fr(dir + "/SPGEMM_RESULT_ROWS.txt"), fc(dir + "/SPGEMM_RESULT_COLS.txt"), fv(dir + "/SPGEMM_RESULT_VALS.txt");
+        // one value per line, formatted and written by all host threads inside the library (pem_write_lines_*: the
+        // reference streams one `<<` per line, spgemm.cu:1549-1558, which is slower than the SpGEMM by orders of magnitude)
+        const std::string fr = dir + "/SPGEMM_RESULT_ROWS.txt", fc = dir + "/SPGEMM_RESULT_COLS.txt", fv = dir + "/SPGEMM_RESULT_VALS.txt";
+        bool written = true;
         for (int pn = 0; pn < PANELS; ++pn) {            // panels in order = rows in order
             if (PANELS > 1) {                             // only the last panel is still alive: recompute the others
                 pem_result_free(ctx, C); C = nullptr;
@@ -235,12 +214,11 @@ int main(int argc, char* argv[])
             std::vector<double> v((size_t)pi.nnz);
             rc = pem_result_to_coo(ctx, C, r.data(), c.data(), v.data());
             DIE_IF(rc, ctx, "COO export");
-            for (auto x : r) fr.put(x);
-            for (auto x : c) fc.put(x);
-            for (auto x : v) fv.put(x);
+            written = pem_write_lines_i32(fr.c_str(), r.data(), pi.nnz, pn > 0) == PEM_OK && written;     // panels after the first append
+            written = pem_write_lines_i32(fc.c_str(), c.data(), pi.nnz, pn > 0) == PEM_OK && written;
+            written = pem_write_lines_f64(fv.c_str(), v.data(), pi.nnz, pn > 0) == PEM_OK && written;
         }
-        const bool okr = fr.close(), okc = fc.close(), okv = fv.close();
-        if (!okr || !okc || !okv) exit_code = 2;
+        if (!written) exit_code = 2;
     }
     std::cout << "CLEANING UP RESOURCES\n\n";
     pem_result_free(ctx, C);

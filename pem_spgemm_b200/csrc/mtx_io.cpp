@@ -7,18 +7,32 @@
 // a symmetric file is emitted ONCE (no extra zero-valued duplicate): duplicates are undefined
 // input for the tile conversion.
 //
-// The body is parsed by all host threads: the file is read in one piece, cut at line boundaries
-// into one chunk per thread, lines are counted, then parsed with std::from_chars straight into
-// the output arrays at each chunk's offset.
+// The body is parsed by all host threads: the file is mapped (no read into a staging buffer: the page
+// faults of the mapping are taken by the parsing threads, in parallel), cut at line boundaries into one
+// chunk per thread, lines are counted, then parsed with std::from_chars straight into the output arrays at
+// each chunk's offset.
+//
+// The writers (Matrix Market files, and the one-number-per-line files of the reference's COO dump,
+// spgemm.cu:1545-1560) format with std::to_chars on all host threads: every thread fills its own buffer with
+// a slice of the lines, the byte offsets follow from the slice lengths, and the threads write their slices
+// with pwrite at those offsets.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include "fixed17.h"
 #include "pemspgemm.h"
 
 namespace {
@@ -72,6 +86,87 @@ inline bool blank_or_comment(const char* p, const char* e)
     return p >= e || *p == '%' || *p == '\n';
 }
 
+// a read-only mapping of a whole file
+struct Mapping {
+    const char* p = nullptr;
+    size_t n = 0;
+    ~Mapping() { if (p && n) munmap(const_cast<char*>(p), n); }
+};
+
+bool write_all(int fd, const char* b, size_t n, long long at)
+{
+    while (n) {
+        const ssize_t w = pwrite(fd, b, n, (off_t)at);
+        if (w <= 0) return false;
+        b += w; n -= (size_t)w; at += w;
+    }
+    return true;
+}
+
+// n lines, formatted by fmt(i, p) -> end of line i (at most max_len bytes, newline included), appended to fd at
+// byte `at`.  Rounds of nt slices: every thread formats its slice of the round, learns its byte offset from the
+// lengths of the slices before it, writes the slice with pwrite and goes on to the next round without waiting for
+// the others' writes (writes to one file serialise in the kernel; the formatting of the next round runs under them).
+// Returns the end offset, or -1 on a write error.
+template <class Fmt>
+long long write_lines(int fd, long long at, int64_t n, size_t max_len, Fmt fmt)
+{
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    if (n < (1 << 16)) nt = 1;
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>((n + nt - 1) / nt, 1 << 18));   // lines per slice
+    const int64_t rounds = (n + per * nt - 1) / (per * nt);
+    std::vector<size_t> len((size_t)2 * nt);              // slice lengths of the even / odd rounds
+    std::atomic<long long> formatted{0};                  // slices formatted so far, all rounds
+    std::atomic<bool> ok{true};
+    std::vector<long long> end_at(nt, at);
+    auto work = [&](unsigned t) {
+        std::vector<char> b;
+        long long base = at;                              // where the current round starts in the file
+        for (int64_t r = 0; r < rounds; ++r) {
+            const int64_t lo = std::min<int64_t>(n, (r * nt + t) * per), hi = std::min<int64_t>(n, lo + per);
+            if (b.size() < max_len) b.resize(std::max<size_t>(max_len, (size_t)(hi - lo) * 24));
+            size_t pos = 0;
+            for (int64_t i = lo; i < hi; ++i) {
+                if (b.size() - pos < max_len) b.resize(b.size() * 2);
+                pos = (size_t)(fmt(i, b.data() + pos) - b.data());
+            }
+            size_t* L = len.data() + (size_t)(r & 1) * nt;
+            L[t] = pos;
+            formatted.fetch_add(1, std::memory_order_release);
+            while (formatted.load(std::memory_order_acquire) < (r + 1) * (long long)nt) std::this_thread::yield();
+            long long mine = base;
+            for (unsigned u = 0; u < nt; ++u) {
+                if (u == t) mine = base;
+                base += (long long)L[u];
+            }
+            if (pos && !write_all(fd, b.data(), pos, mine)) ok = false;
+        }
+        end_at[t] = base;
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    return ok ? end_at[0] : -1;
+}
+
+// open for a fresh file or for appending; *at = the offset the new lines start at
+int open_out(const char* path, int append, long long* at)
+{
+    const int fd = open(path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
+    if (fd < 0) return -1;
+    *at = 0;
+    if (append) {
+        const off_t e = lseek(fd, 0, SEEK_END);
+        if (e < 0) { close(fd); return -1; }
+        *at = (long long)e;
+    }
+    return fd;
+}
+
 }  // namespace
 
 extern "C" {
@@ -83,18 +178,24 @@ int pem_mtx_read(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz,
 {
     if (!path || !rows || !cols || !nnz || !I || !J || !V) return PEM_ERR_ARG;
     *I = *J = nullptr; *V = nullptr;
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_err(err, err_len, std::string("cannot open ") + path); return PEM_ERR_IO; }
-    fseek(f, 0, SEEK_END);
-    long long fsz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> buf((size_t)fsz + 1);
-    size_t got = fread(buf.data(), 1, (size_t)fsz, f);
-    fclose(f);
-    if ((long long)got != fsz) { set_err(err, err_len, "short read"); return PEM_ERR_IO; }
-    buf[(size_t)fsz] = '\n';
-    const char* p = buf.data();
-    const char* end = buf.data() + fsz;
+    Mapping map;
+    {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) { set_err(err, err_len, std::string("cannot open ") + path); return PEM_ERR_IO; }
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); set_err(err, err_len, std::string("cannot read ") + path); return PEM_ERR_IO; }
+        if (st.st_size > 0) {
+            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { close(fd); set_err(err, err_len, std::string("cannot map ") + path); return PEM_ERR_IO; }
+            map.p = (const char*)m; map.n = (size_t)st.st_size;
+            madvise(m, map.n, MADV_WILLNEED);
+        }
+        close(fd);
+    }
+    // every scan below is bounded by `end` (memchr, from_chars), so the mapping needs no terminator
+    const char* p = map.p;
+    const char* end = map.p + map.n;
+    if (!map.n) { set_err(err, err_len, "missing %%MatrixMarket banner"); return PEM_ERR_IO; }
 
     // banner
     const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
@@ -207,23 +308,53 @@ int pem_mtx_write(const char* path, int32_t rows, int32_t cols, int64_t nnz,
                   const int32_t* I, const int32_t* J, const double* V)
 {
     if (!path || nnz < 0 || (nnz && (!I || !J || !V))) return PEM_ERR_ARG;
-    FILE* f = fopen(path, "wb");
-    if (!f) return PEM_ERR_IO;
-    fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n%d %d %lld\n", rows, cols, (long long)nnz);
-    std::vector<char> buf(1 << 22);
-    size_t pos = 0;
-    for (int64_t e = 0; e < nnz; ++e) {
-        if (pos + 96 > buf.size()) { fwrite(buf.data(), 1, pos, f); pos = 0; }
-        char* q = buf.data() + pos;
-        q = std::to_chars(q, q + 16, I[e] + 1).ptr; *q++ = ' ';
-        q = std::to_chars(q, q + 16, J[e] + 1).ptr; *q++ = ' ';
-        q = std::to_chars(q, q + 40, V[e]).ptr; *q++ = '\n';   // shortest round-trip representation
-        pos = (size_t)(q - buf.data());
-    }
-    fwrite(buf.data(), 1, pos, f);
-    int rc = ferror(f) ? PEM_ERR_IO : PEM_OK;
-    fclose(f);
-    return rc;
+    long long at = 0;
+    const int fd = open_out(path, 0, &at);
+    if (fd < 0) return PEM_ERR_IO;
+    char head[128];
+    const int hn = snprintf(head, sizeof head, "%%%%MatrixMarket matrix coordinate real general\n%d %d %lld\n", rows, cols, (long long)nnz);
+    bool ok = write_all(fd, head, (size_t)hn, 0);
+    if (ok)
+        ok = write_lines(fd, hn, nnz, 96, [&](int64_t e, char* q) {
+                 q = std::to_chars(q, q + 16, I[e] + 1).ptr; *q++ = ' ';
+                 q = std::to_chars(q, q + 16, J[e] + 1).ptr; *q++ = ' ';
+                 q = std::to_chars(q, q + 40, V[e]).ptr; *q++ = '\n';   // shortest round-trip representation
+                 return q;
+             }) >= 0;
+    ok = (close(fd) == 0) && ok;
+    return ok ? PEM_OK : PEM_ERR_IO;
+}
+
+// One number per line: the files of the reference's COO dump (spgemm.cu:1545-1560).  Integers as they are;
+// doubles in fixed notation with max_digits10 = 17 decimals, the digits `std::fixed << std::setprecision(17)`
+// prints there.  append != 0 continues an existing file (results dumped panel by panel).
+int pem_write_lines_i32(const char* path, const int32_t* x, int64_t n, int append)
+{
+    if (!path || n < 0 || (n && !x)) return PEM_ERR_ARG;
+    long long at = 0;
+    const int fd = open_out(path, append, &at);
+    if (fd < 0) return PEM_ERR_IO;
+    bool ok = write_lines(fd, at, n, 16, [&](int64_t i, char* q) {
+                  q = std::to_chars(q, q + 15, x[i]).ptr; *q++ = '\n';
+                  return q;
+              }) >= 0;
+    ok = (close(fd) == 0) && ok;
+    return ok ? PEM_OK : PEM_ERR_IO;
+}
+
+int pem_write_lines_f64(const char* path, const double* x, int64_t n, int append)
+{
+    if (!path || n < 0 || (n && !x)) return PEM_ERR_ARG;
+    long long at = 0;
+    const int fd = open_out(path, append, &at);
+    if (fd < 0) return PEM_ERR_IO;
+    bool ok = write_lines(fd, at, n, 400, [&](int64_t i, char* q) {      // 1.8e308 in fixed notation: 309 + 1 + 17 digits
+                  q = pem_fmt::fixed17(x[i], q);      // printf("%.17f") digits from integer arithmetic (fixed17.h)
+                  *q++ = '\n';
+                  return q;
+              }) >= 0;
+    ok = (close(fd) == 0) && ok;
+    return ok ? PEM_OK : PEM_ERR_IO;
 }
 
 }  // extern "C"

@@ -84,3 +84,70 @@ def test_mtx_large_parallel_parse(tmp_path):
     assert os.path.getsize(p) > (1 << 20)           # takes the multi-threaded path
     r2, c2, I2, J2, V2, _ = pem.mtx_read(p)
     assert np.array_equal(I, I2) and np.array_equal(J, J2) and np.array_equal(V, V2)
+
+
+def test_mtx_reader_edge_files(tmp_path):
+    """The reader maps the file: no terminator behind the last byte, CRLF line ends, blank lines, an empty file,
+    a header-only file."""
+    e = tmp_path / "e.mtx"
+    e.write_bytes(b"")
+    with pytest.raises(pem.PemError):
+        pem.mtx_read(str(e))
+    n = tmp_path / "n.mtx"
+    n.write_bytes(b"%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.5\n2 2 -2.25")   # no final newline
+    r, c, I, J, V, _ = pem.mtx_read(str(n))
+    assert (r, c, list(I), list(J), list(V)) == (2, 2, [0, 1], [0, 1], [1.5, -2.25])
+    w = tmp_path / "w.mtx"
+    w.write_bytes(b"%%MatrixMarket matrix coordinate integer general\r\n% c\r\n\r\n3 2 2\r\n\r\n3 1 7\r\n1 2 +4\r\n")
+    r, c, I, J, V, _ = pem.mtx_read(str(w))
+    assert (r, c, list(I), list(J), list(V)) == (3, 2, [2, 0], [0, 1], [7.0, 4.0])
+    z = tmp_path / "z.mtx"
+    z.write_bytes(b"%%MatrixMarket matrix coordinate real general\n4 5 0\n")
+    r, c, I, J, V, _ = pem.mtx_read(str(z))
+    assert (r, c, I.size) == (4, 5, 0)
+    h = tmp_path / "h.mtx"
+    h.write_bytes(b"%%MatrixMarket matrix coordinate real general")
+    with pytest.raises(pem.PemError):
+        pem.mtx_read(str(h))
+
+
+def _fixed17(x):
+    return "%.17f" % x          # the digits `std::fixed << std::setprecision(17)` prints (spgemm.cu:1529)
+
+
+def test_dump_lines_match_the_reference_format(tmp_path):
+    """pem_write_lines_*: one number per line, doubles as the reference's dump prints them."""
+    vals = np.array([0.0, -0.0, 1.0, -1.5, 0.1, 1.0 / 3.0, 2.5e-17, 4.9e-18, 5e-324, 1e-20, 123456789.123456789, 1e22,
+                     -7.000000000000001, 0.5, 0.49999999999999994, 1e15 + 0.3, 2.0 ** 53, 2.0 ** 53 + 2, 1.7976931348623157e308,
+                     65536.000000000001, 1e-5, 3.0000000000000004e-5, 999999.99999999988], np.float64)
+    p = str(tmp_path / "v.txt")
+    pem.write_lines(p, vals)
+    assert open(p).read() == "".join(_fixed17(x) + "\n" for x in vals)
+    ints = np.array([0, 1, -1, 2147483647, -2147483648, 10, 99, 100, 123456789], np.int32)
+    q = str(tmp_path / "i.txt")
+    pem.write_lines(q, ints)
+    assert open(q).read() == "".join(f"{int(x)}\n" for x in ints)
+    pem.write_lines(q, ints[:3], append=True)                      # a second panel continues the file
+    assert open(q).read() == "".join(f"{int(x)}\n" for x in list(ints) + list(ints[:3]))
+    pem.write_lines(q, ints[:2])                                   # and a fresh dump truncates it
+    assert open(q).read() == "0\n1\n"
+    pem.write_lines(q, ints[:0])
+    assert open(q).read() == ""
+
+
+def test_dump_lines_parallel_slices_keep_order(tmp_path):
+    """More lines than one slice: every host thread formats a slice and writes it at its own offset."""
+    rng = np.random.default_rng(11)
+    n = 700_000
+    vals = np.concatenate([rng.uniform(-1, 1, n // 2), rng.standard_normal(n // 4) * 1e6,
+                           rng.uniform(0, 1, n // 4) * 10.0 ** rng.integers(-25, 12, n // 4)])
+    p = str(tmp_path / "v.txt")
+    pem.write_lines(p, vals)
+    assert open(p).read() == "".join(_fixed17(x) + "\n" for x in vals)
+    pem.write_lines(p, vals[:100_000], append=True)
+    got = open(p).read().split("\n")
+    assert len(got) == n + 100_000 + 1 and got[n] == _fixed17(vals[0]) and got[-2] == _fixed17(vals[99_999])
+    ints = rng.integers(-2 ** 31, 2 ** 31, n, dtype=np.int64).astype(np.int32)
+    q = str(tmp_path / "i.txt")
+    pem.write_lines(q, ints)
+    assert np.array_equal(np.loadtxt(q, dtype=np.int64), ints.astype(np.int64))

@@ -541,11 +541,9 @@ static int launch_windows(pem_ctx* ctx, const pem_tiled* A, const pem_tiled* B, 
     PEM_LAUNCHED();
     auto kern = k_step3_windows<T, NP, SCAP, ECAP, MINB, HITS>;
     constexpr int smem = S3WLayout<NP, SCAP, ECAP>::BYTES;
-    static bool attr_set = false;                               // opt in to > 48 KB of dynamic shared memory (once per process)
-    if (!attr_set && smem > 48 * 1024) {
-        PEM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    // window shapes above 48 KB of dynamic shared memory opt in (per launch: the attribute belongs to the device the
+    // context runs on, and a process may hold one context per GPU; the shipped 26 KB shape compiles this away)
+    if constexpr (smem > 48 * 1024) PEM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     KT_BEGIN(KT_NUMERIC);
     kern<<<(unsigned)n_windows, S3W_THREADS, smem, ctx->stream>>>(
         win_tile, C->tile_nnz_ptr, reinterpret_cast<const uint4*>(C->masks), C->pair_ptr, C->pair_list, C->pair_hit,

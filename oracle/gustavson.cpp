@@ -98,7 +98,7 @@ int64_t oracle_spgemm_symbolic(int m, int n, const int64_t* Ap, const int* Aj,
 #pragma omp parallel
     {
         std::vector<int> mark((size_t)n, -1);
-#pragma omp for schedule(dynamic, 16)
+#pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < m; ++i) {
             int64_t cnt = 0;
             for (int64_t p = Ap[i]; p < Ap[i + 1]; ++p) {
@@ -125,7 +125,7 @@ void oracle_spgemm_numeric(int m, int n, const int64_t* Ap, const int* Aj, const
     {
         std::vector<int> mark((size_t)n, -1);
         std::vector<double> acc((size_t)n, 0.0);
-#pragma omp for schedule(dynamic, 16)
+#pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < m; ++i) {
             int64_t base = Cp[i], cnt = 0;
             for (int64_t p = Ap[i]; p < Ap[i + 1]; ++p) {
@@ -157,7 +157,7 @@ void oracle_spgemm_numeric_f32(int m, int n, const int64_t* Ap, const int* Aj, c
     {
         std::vector<int> mark((size_t)n, -1);
         std::vector<float> acc((size_t)n, 0.0f);
-#pragma omp for schedule(dynamic, 16)
+#pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < m; ++i) {
             int64_t base = Cp[i], cnt = 0;
             for (int64_t p = Ap[i]; p < Ap[i + 1]; ++p) {

@@ -151,3 +151,67 @@ def test_dump_lines_parallel_slices_keep_order(tmp_path):
     q = str(tmp_path / "i.txt")
     pem.write_lines(q, ints)
     assert np.array_equal(np.loadtxt(q, dtype=np.int64), ints.astype(np.int64))
+
+
+def test_mtx_reader_fuzz_against_a_python_parser(tmp_path):
+    """Seeded fuzz of the reader: every field / symmetry combination, random spacing (blanks, tabs, CRLF), comment and
+    blank lines between entries, signs and exponents in every spelling from_chars / strtod accept; compared with a
+    line-by-line Python parse of the same text."""
+    rng = np.random.default_rng(2024)
+
+    def num(x):
+        style = rng.integers(0, 5)
+        if style == 0:
+            return repr(float(x))
+        if style == 1:
+            return "%.17e" % x
+        if style == 2:
+            return ("+" if x >= 0 else "") + "%.6f" % x
+        if style == 3:
+            return "%dE0" % int(x) if float(x).is_integer() else "%.10g" % x
+        return "%.3E" % x
+
+    for case in range(40):
+        field = ["real", "integer", "pattern", "complex"][case % 4]
+        symm = ["general", "symmetric", "skew-symmetric"][(case // 4) % 3]
+        rows = int(rng.integers(1, 40))
+        cols = rows if symm != "general" else int(rng.integers(1, 40))
+        cells = [(i, j) for i in range(rows) for j in range(cols)
+                 if symm == "general" or j < i or (j == i and symm == "symmetric")]
+        take = rng.permutation(len(cells))[: int(rng.integers(0, min(len(cells), 60) + 1))]
+        sep = lambda: "".join(rng.choice([" ", "\t", "  "], size=int(rng.integers(1, 3))))
+        eol = "\r\n" if case % 5 == 0 else "\n"
+        lines, want = [], {}
+        for t in take:
+            i, j = cells[int(t)]
+            v = float(rng.integers(-50, 50)) if field == "integer" else float(np.round(rng.normal() * 10.0 ** int(rng.integers(-8, 8)), 12))
+            if field == "pattern":
+                txt, v = "", 1.0
+            elif field == "integer":
+                txt = sep() + ("+%d" % v if v > 0 and rng.random() < 0.3 else "%d" % v)
+            elif field == "complex":
+                txt = sep() + num(v) + sep() + num(rng.normal())
+                v = float(txt.split()[0])
+            else:
+                txt = sep() + num(v)
+                v = float(txt.split()[0])
+            lead = sep() if rng.random() < 0.2 else ""
+            lines.append(f"{lead}{i + 1}{sep()}{j + 1}{txt}" + (sep() if rng.random() < 0.2 else ""))
+            if rng.random() < 0.1:
+                lines.append("% a comment between entries")
+            if rng.random() < 0.1:
+                lines.append("")
+            want[(i, j)] = v
+            if symm != "general" and i != j:
+                want[(j, i)] = -v if symm == "skew-symmetric" else v
+        text = f"%%MatrixMarket matrix coordinate {field} {symm}{eol}% generated{eol}{eol}{rows} {cols} {len(take)}{eol}"
+        text += "".join(l + eol for l in lines)
+        if case % 7 == 0 and lines:
+            text = text[: -len(eol)]                      # no terminator behind the last entry
+        p = tmp_path / f"f{case}.mtx"
+        p.write_bytes(text.encode())
+        r, c, I, J, V, sym = pem.mtx_read(str(p))
+        got = {(int(a), int(b)): float(v) for a, b, v in zip(I, J, V)}
+        assert (r, c) == (rows, cols) and I.size == len(want), (case, field, symm)
+        assert got == want, (case, field, symm)
+        assert sym == (symm == "symmetric")

@@ -9,8 +9,8 @@
 //
 // The body is parsed by all host threads: the file is mapped (no read into a staging buffer: the page
 // faults of the mapping are taken by the parsing threads, in parallel), cut at line boundaries into one
-// chunk per thread, lines are counted, then parsed with std::from_chars straight into the output arrays at
-// each chunk's offset.
+// chunk per thread, the chunks' lines are counted as newline bytes, and every chunk is parsed in ONE pass
+// (digit loops for the coordinates, std::from_chars for the value) straight into its place of the output.
 //
 // The writers (Matrix Market files, and the one-number-per-line files of the reference's COO dump,
 // spgemm.cu:1545-1560) format with std::to_chars on all host threads: every thread fills its own buffer with
@@ -249,51 +249,97 @@ int pem_mtx_read(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz,
             b = e;
         }
     }
-    auto for_each_line = [](Chunk& c, auto&& fn) {
-        const char* q = c.b;
-        while (q < c.e) {
-            const char* nl = (const char*)memchr(q, '\n', (size_t)(c.e - q));
-            if (!nl) nl = c.e;
-            if (!blank_or_comment(q, nl)) fn(q, nl);
-            q = nl + 1;
+    // Lines per chunk, counted as newline bytes (a vectorised compare-and-add, several GB/s per thread): an upper
+    // bound of the chunk's entries that is exact unless the body holds blank or comment lines, so every chunk can be
+    // parsed straight into its place of the output; the rare gaps are closed afterwards.
+    auto count_lines = [&](unsigned t) {
+        const char* b = ch[t].b;
+        const char* const e = ch[t].e;
+        size_t n = 0;
+        if (b < e && e[-1] != '\n') n = 1;                   // the file's last line has no terminator
+        while (b < e) {
+            const size_t m = std::min<size_t>((size_t)(e - b), 4096);
+            unsigned k = 0;
+            for (size_t x = 0; x < m; ++x) k += (b[x] == '\n');
+            n += k;
+            b += m;
         }
+        ch[t].lines = n;
     };
-    {
+    auto on_threads = [&](auto&& fn) {
+        if (nt == 1) { fn(0u); return; }
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t)
-            th.emplace_back([&, t] { for_each_line(ch[t], [&](const char*, const char*) { ++ch[t].lines; }); });
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
         for (auto& x : th) x.join();
-    }
-    size_t total = 0;
-    for (auto& c : ch) { c.out = total; total += c.lines; }
-    if ((long long)total != N) { set_err(err, err_len, "entry count differs from the size line"); return PEM_ERR_IO; }
-    const size_t cap = (symm || skew) ? 2 * total : total;
+    };
+    on_threads(count_lines);
+    size_t room = 0;
+    for (auto& c : ch) { c.out = room; room += c.lines; }
+    if ((long long)room < N) { set_err(err, err_len, "entry count differs from the size line"); return PEM_ERR_IO; }
+    const size_t cap = (symm || skew) ? 2 * room : room;
     int32_t* oi = (int32_t*)malloc(std::max<size_t>(cap, 1) * 4);
     int32_t* oj = (int32_t*)malloc(std::max<size_t>(cap, 1) * 4);
     double* ov = (double*)malloc(std::max<size_t>(cap, 1) * 8);
     if (!oi || !oj || !ov) { free(oi); free(oj); free(ov); set_err(err, err_len, "out of host memory"); return PEM_ERR_IO; }
-    {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t)
-            th.emplace_back([&, t] {
-                size_t o = ch[t].out;
-                for_each_line(ch[t], [&](const char* q, const char* nl) {
-                    long long i = 0, j = 0;
-                    double v = 1.0;
-                    bool ok = true;
-                    q = parse_i64(q, nl, i, ok);
-                    q = parse_i64(q, nl, j, ok);
-                    if (!pattern) q = parse_f64(q, nl, v, ok);  // complex: the real part comes first
-                    if (!ok || i < 1 || j < 1 || i > R || j > Cc) { ch[t].ok = false; i = j = 1; }
-                    oi[o] = (int32_t)(i - 1); oj[o] = (int32_t)(j - 1); ov[o] = v;
-                    ++o;
-                });
-            });
-        for (auto& x : th) x.join();
-    }
+    // One pass per chunk, no line search up front: coordinates by a digit loop, the value by from_chars (which stops
+    // at the line end by itself), then on to the newline.  An entry uses up at least one line, so a chunk never
+    // writes past its room.
+    std::vector<size_t> found(nt, 0);
+    auto parse_chunk = [&](unsigned t) {
+        Chunk& c = ch[t];
+        size_t o = c.out;
+        const char* q = c.b;
+        const char* const e = c.e;
+        auto coord = [&](long long lim, int32_t& out) {    // [ws] [+] digits, 1 <= value <= lim
+            q = skip_ws(q, e);
+            if (q < e && *q == '+') ++q;
+            unsigned long long x = 0;
+            const char* d0 = q;
+            while (q < e && (unsigned)(*q - '0') < 10u && q - d0 < 18) x = x * 10 + (unsigned)(*q++ - '0');
+            if (q == d0 || (q < e && (unsigned)(*q - '0') < 10u) || x < 1 || x > (unsigned long long)lim) { c.ok = false; out = 0; return; }
+            out = (int32_t)(x - 1);
+        };
+        while (q < e) {
+            q = skip_ws(q, e);
+            if (q < e && *q != '\n' && *q != '%') {
+                double v = 1.0;
+                coord(R, oi[o]);
+                coord(Cc, oj[o]);
+                if (!pattern && c.ok) {                      // complex: the real part comes first
+                    q = skip_ws(q, e);
+                    if (q < e && *q == '+') ++q;
+                    auto r = std::from_chars(q, e, v);
+                    if (r.ec == std::errc()) {
+                        q = r.ptr;
+                    } else {                                 // inf / nan spellings, exotic formats: strtod on this line only
+                        const char* nl = (const char*)memchr(q, '\n', (size_t)(e - q));
+                        bool ok = true;
+                        q = parse_f64(q, nl ? nl : e, v, ok);
+                        if (!ok) c.ok = false;
+                    }
+                }
+                ov[o] = v;
+                ++o;
+            }
+            const char* nl = (const char*)memchr(q, '\n', (size_t)(e - q));     // rest of the line (usually nothing)
+            q = nl ? nl + 1 : e;
+        }
+        found[t] = o - c.out;
+    };
+    on_threads(parse_chunk);
     (void)complex_;
     for (auto& c : ch)
         if (!c.ok) { free(oi); free(oj); free(ov); set_err(err, err_len, "malformed or out-of-range entry"); return PEM_ERR_IO; }
+    size_t total = 0;
+    for (unsigned t = 0; t < nt; ++t) {                     // close the gaps blank / comment lines left (usually none)
+        if (found[t] && total != ch[t].out) {
+            memmove(oi + total, oi + ch[t].out, found[t] * 4);
+            memmove(oj + total, oj + ch[t].out, found[t] * 4);
+            memmove(ov + total, ov + ch[t].out, found[t] * 8);
+        }
+        total += found[t];
+    }
+    if ((long long)total != N) { free(oi); free(oj); free(ov); set_err(err, err_len, "entry count differs from the size line"); return PEM_ERR_IO; }
     size_t n = total;
     if (symm || skew) {
         for (size_t e = 0; e < total; ++e)

@@ -215,3 +215,34 @@ def test_mtx_reader_fuzz_against_a_python_parser(tmp_path):
         assert (r, c) == (rows, cols) and I.size == len(want), (case, field, symm)
         assert got == want, (case, field, symm)
         assert sym == (symm == "symmetric")
+
+
+def test_mtx_large_parallel_parse_with_comment_and_blank_lines(tmp_path):
+    """Multi-threaded reader on a body that holds comment and blank lines: every chunk's room is the count of its
+    newline bytes, so the chunks behind such lines have to move down when the gaps are closed."""
+    rows, cols, I, J, V = synth.random_sparse(40_000, 30_000, 200_000, seed=12)
+    p = str(tmp_path / "big.mtx")
+    pem.mtx_write(p, rows, cols, I, J, V)
+    text = open(p).read().split("\n")
+    head, body = text[:2], text[2:]
+    assert body[-1] == ""
+    body = body[:-1]
+    rng = np.random.default_rng(3)
+    out = []
+    for k, line in enumerate(body):
+        out.append(line)
+        if k % 997 == 0:
+            out.append("% comment in the body")
+        if k % 1499 == 0:
+            out.append("" if rng.random() < 0.5 else "  \t ")
+    q = tmp_path / "big2.mtx"
+    q.write_text("\n".join(head + out))                    # and no newline behind the last entry
+    assert os.path.getsize(q) > (1 << 20)
+    r2, c2, I2, J2, V2, _ = pem.mtx_read(str(q))
+    assert (r2, c2) == (rows, cols)
+    assert np.array_equal(I, I2) and np.array_equal(J, J2) and np.array_equal(V, V2)
+    # one entry too few / too many for the size line is still an error
+    bad = tmp_path / "big3.mtx"
+    bad.write_text("\n".join(head + out[:-1]))
+    with pytest.raises(pem.PemError):
+        pem.mtx_read(str(bad))
